@@ -1,0 +1,27 @@
+# Builds librakau_b200.so (sm_100a only) and the oracle. `python -c "import __graft_entry__ as g; g.build()"` calls this.
+NVCC     ?= /usr/local/cuda/bin/nvcc
+ARCH      = -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v --expt-relaxed-constexpr
+CSRC      = rakau_b200/csrc
+OBJDIR    = build
+LIB       = rakau_b200/lib/librakau_b200.so
+OBJS      = $(OBJDIR)/sort.o $(OBJDIR)/build.o $(OBJDIR)/traverse.o $(OBJDIR)/capi.o
+
+all: $(LIB) oracle
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/scan.cuh include/rakau_b200.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJS)
+	@mkdir -p rakau_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf $(OBJDIR) $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

@@ -1,0 +1,167 @@
+/* rakau_b200.h — C ABI of librakau_b200.so, the B200 (sm_100a) implementation of rakau's Barnes-Hut hot path.
+ *
+ * This is the drop-in boundary. The reference has exactly one accelerator seam,
+ *   include/rakau/detail/cuda_fwd.hpp:23-30   cuda_min_size / cuda_device_count / cuda_acc_pot_impl<Q,NDim,F,UInt,MAC>
+ * called from include/rakau/tree.hpp:3135,3191,3207,3220 (traversal only; build is CPU-only in the reference).
+ * The entry points below replace that seam (rk_min_size, rk_device_count, rk_traverse_external_tree) and
+ * add the seam the reference lacks: a device-resident tree (Morton encode, sort, octree build, node
+ * properties — reference construct_impl tree.hpp:1329-1487, build_tree 932-1111, sync 3678-3743) whose
+ * traversal (acc_pot_impl 2853-3265) never leaves the GPU.
+ *
+ * Conventions
+ *  - plain C types only; floating-point arrays are `const void*`/`void*` holding float (fp_bits=32) or
+ *    double (fp_bits=64), matching the tree's precision;
+ *  - every function returning int returns an rk_status; on error rk_last_error(tree) holds the message the
+ *    C++ wrapper (include/rakau/tree.hpp in this repo) rethrows as the reference's exception type;
+ *  - a tree handle owns all of its device state; const operations on one handle are serialised internally;
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with RK_ERR_RUNTIME.
+ */
+#ifndef RAKAU_B200_H
+#define RAKAU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RK_API __attribute__((visibility("default")))
+#else
+#define RK_API
+#endif
+
+typedef enum rk_status {
+    RK_OK = 0,
+    RK_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference */
+    RK_ERR_DOMAIN = 2,           /* std::domain_error (theta / eps / G checks, tree.hpp:3268-3317) */
+    RK_ERR_OVERFLOW = 3,         /* std::overflow_error */
+    RK_ERR_RUNTIME = 4,          /* std::runtime_error (any CUDA failure, rakau_cuda.cu:83-127) */
+    RK_ERR_BAD_ALLOC = 5         /* std::bad_alloc (rakau_cuda.cu:47-55) */
+} rk_status;
+
+enum { RK_MAC_BH = 0, RK_MAC_BH_GEOM = 1 };       /* rakau::mac, detail/tree_fwd.hpp:46 */
+enum { RK_Q_ACCS = 0, RK_Q_POTS = 1, RK_Q_ACCS_POTS = 2 }; /* Q, detail/tree_fwd.hpp:129-137 */
+enum { RK_PERM = 0, RK_LAST_PERM = 1, RK_INV_PERM = 2 };
+enum { RK_HOST = 0, RK_DEVICE = 1 };
+
+typedef struct rk_tree rk_tree;
+
+/* Node as returned to the host: field order of base_tree_node_t + tree_node_t (detail/tree_fwd.hpp:76-116).
+ * `dim` is dim2 for RK_MAC_BH and dim for RK_MAC_BH_GEOM; `delta` is 0 for RK_MAC_BH. */
+typedef struct rk_node_f32 {
+    uint64_t begin, end, n_children, code, level;
+    float props[4], dim, delta;
+} rk_node_f32;
+typedef struct rk_node_f64 {
+    uint64_t begin, end, n_children, code, level;
+    double props[4], dim, delta;
+} rk_node_f64;
+/* Critical node, tree_cnode_t (detail/tree_fwd.hpp:119-125). */
+typedef struct rk_cnode {
+    uint64_t code, begin, end;
+} rk_cnode;
+
+typedef struct rk_build_info {
+    double box_size;      /* deduced or given */
+    uint64_t n_nodes;     /* tree size */
+    uint64_t n_crit;      /* critical nodes */
+    uint64_t max_group;   /* largest critical node */
+    uint32_t sort_passes; /* radix passes actually run */
+    float ms_total;       /* CUDA-event time of the whole build on the tree's stream */
+    float ms_encode, ms_sort, ms_permute, ms_topology, ms_props;
+} rk_build_info;
+
+typedef struct rk_eval_info {
+    uint64_t mac_tests;    /* node MAC evaluations (group level) */
+    uint64_t accepted;     /* accepted nodes */
+    uint64_t p2p_pairs;    /* target x leaf-particle pairs */
+    uint64_t self_pairs;   /* unordered pairs inside the groups */
+    uint64_t interactions; /* sum over groups of tgt*(leaf sources + accepted + tgt-1), SURVEY §8(d) */
+    uint64_t n_groups;     /* groups evaluated by this call */
+    uint32_t kernel_launches;
+    float ms_kernel;       /* CUDA-event time of the traversal kernel(s) only */
+    float ms_total;        /* kernel + output scatter/copies issued by the call */
+} rk_eval_info;
+
+/* ---- the reference's seam ---------------------------------------------------------------------------- */
+/* cuda_device_count(), src/rakau_cuda.cu:32 — 0 on any CUDA error. */
+RK_API unsigned rk_device_count(void);
+/* cuda_min_size(), src/rakau_cuda.cu:26 — minimum number of particles worth sending to a GPU. */
+RK_API unsigned rk_min_size(void);
+
+/* ---- tree lifetime ----------------------------------------------------------------------------------- */
+RK_API rk_tree *rk_tree_create(int fp_bits, int mac, int device);
+RK_API void rk_tree_destroy(rk_tree *t);
+RK_API const char *rk_last_error(const rk_tree *t);
+/* Message of the last failed rk_tree_create (no handle exists to ask). */
+RK_API const char *rk_create_error(void);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this tree. */
+RK_API int rk_tree_set_stream(rk_tree *t, void *cuda_stream);
+RK_API int rk_tree_synchronize(rk_tree *t);
+
+/* ---- construction: construct_impl, tree.hpp:1329-1487 ------------------------------------------------ */
+/* Copies n particles (SoA x, y, z, m; host or device pointers) into the tree, deduces the box if
+ * `deduce_box` (determine_box_size, tree.hpp:1278-1319), Morton-encodes (disc_single_coord 381-429 +
+ * morton_encoder 222-242), stable-sorts (indirect_code_sort 1266-1274), permutes (apply_isort 484-507),
+ * builds nodes + critical nodes (build_tree 932-1111) and node properties (compute_node_properties
+ * 1116-1237). */
+RK_API int rk_tree_build(rk_tree *t, const void *x, const void *y, const void *z, const void *m, size_t n, int where,
+                         double box_size, int deduce_box, size_t max_leaf_n, size_t ncrit, rk_build_info *info);
+/* sync(), tree.hpp:3678-3743: new coordinates in the CURRENT Morton order (NULL = unchanged). */
+RK_API int rk_tree_update_positions(rk_tree *t, const void *x, const void *y, const void *z, int where,
+                                    rk_build_info *info);
+/* update_masses_dispatch, tree.hpp:3782-3805: new masses in the current Morton order; topology untouched. */
+RK_API int rk_tree_update_masses(rk_tree *t, const void *m, int where);
+/* clear(), tree.hpp:1882-1904. */
+RK_API int rk_tree_clear(rk_tree *t);
+
+/* ---- getters (lazy D2H) ------------------------------------------------------------------------------ */
+RK_API size_t rk_tree_nparts(const rk_tree *t);
+RK_API size_t rk_tree_nnodes(const rk_tree *t);
+RK_API size_t rk_tree_ncrit(const rk_tree *t);
+RK_API double rk_tree_box_size(const rk_tree *t);
+/* p_its_u(): Morton-ordered SoA (any pointer may be NULL). */
+RK_API int rk_tree_get_parts(rk_tree *t, void *x, void *y, void *z, void *m);
+/* c_it_u(): sorted Morton codes. */
+RK_API int rk_tree_get_codes(rk_tree *t, uint64_t *codes);
+/* perm()/last_perm()/inv_perm(), widened to 64 bit. */
+RK_API int rk_tree_get_perm(rk_tree *t, int which, uint64_t *out);
+/* nodes(): rk_node_f32 / rk_node_f64 array in the reference's DFS pre-order. */
+RK_API int rk_tree_get_nodes(rk_tree *t, void *nodes);
+RK_API int rk_tree_get_crit(rk_tree *t, rk_cnode *crit);
+
+/* ---- traversal: acc_pot_dispatch / acc_pot_impl, tree.hpp:3293-3334, 2853-3265 ----------------------- */
+/* out[0..2] accelerations (Q=0), out[0] potentials (Q=1), out[0..3] accs+pots (Q=2); each of nparts
+ * elements, host or device. ordered=0: Morton order (accs_u ...); ordered=1: original order (accs_o ...).
+ * split/nsplit: the reference's `split` kwarg (validated as tree.hpp:2857-2868); when [crit_begin,crit_end)
+ * is given through rk_tree_acc_pot_range the call evaluates only those critical nodes. */
+RK_API int rk_tree_acc_pot(rk_tree *t, int Q, int ordered, double theta, double G, double eps, const double *split,
+                           size_t nsplit, void *const out[4], int where, rk_eval_info *info);
+/* Evaluate critical nodes [crit_begin, crit_end) only (multi-GPU sharding by Morton range). Outputs are
+ * written for the particles those nodes cover, at their global positions in `out`. */
+RK_API int rk_tree_acc_pot_range(rk_tree *t, int Q, int ordered, double theta, double G, double eps, size_t crit_begin,
+                                 size_t crit_end, void *const out[4], int where, rk_eval_info *info);
+/* Per-critical-node interaction counts of the last full evaluation (cost weights for sharding). */
+RK_API int rk_tree_get_group_costs(rk_tree *t, uint64_t *costs);
+/* exact_acc_pot_impl, tree.hpp:3531-3569: direct sum for one particle. idx in Morton order (ordered=0) or
+ * original order (ordered=1). out4 = ax, ay, az, pot. */
+RK_API int rk_tree_exact(rk_tree *t, size_t idx, int ordered, double G, double eps, double out4[4]);
+
+/* ---- literal drop-in for cuda_acc_pot_impl (cuda_fwd.hpp:27-30, rakau_cuda.cu:348-528) ---------------- */
+/* Stateless: host AoS tree in DFS order (rk_node_f32/f64), host SoA particles in Morton order, host codes.
+ * Evaluates particles [split_indices[0], nparts) like the reference (the GPU share), writing to out[j] at
+ * offset 0 (offset_output=0) or at split_indices[0] (offset_output=1). mac_value is theta^-2 (bh) or
+ * theta^-1 (bh_geom), as passed by tree.hpp:3207. ncrit (not in the reference signature) selects the
+ * target grouping of the CPU path; pass 0 for the reference default (128). */
+RK_API int rk_traverse_external_tree(int fp_bits, int mac, int Q, void *const out[4], const uint64_t *split_indices,
+                                     size_t nsplit, const void *tree, size_t tree_size, const void *const parts[4],
+                                     const uint64_t *codes, size_t nparts, double mac_value, double G, double eps2,
+                                     int offset_output, size_t ncrit, rk_eval_info *info, char *errbuf,
+                                     size_t errbuf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

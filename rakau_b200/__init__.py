@@ -1,0 +1,254 @@
+"""rakau_b200 — thin ctypes plumbing over librakau_b200.so (C ABI in include/rakau_b200.h).
+
+The product is the CUDA library plus the C++17 header include/rakau/tree.hpp (the reference's own
+`rakau::octree<F, MAC>` API). This module only lets Python drive the C ABI for tests, bench.py and
+multi-GPU orchestration with torch.distributed. There is NO CPU fallback: if the shared library is
+missing, or no CUDA device is present, construction fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librakau_b200.so")
+_LIB = None
+
+RK_HOST, RK_DEVICE = 0, 1
+RK_PERM, RK_LAST_PERM, RK_INV_PERM = 0, 1, 2
+FDT = {32: np.float32, 64: np.float64}
+
+NODE_DTYPE = {
+    32: np.dtype([("begin", "<u8"), ("end", "<u8"), ("n_children", "<u8"), ("code", "<u8"), ("level", "<u8"),
+                  ("props", "<f4", (4,)), ("dim", "<f4"), ("delta", "<f4")]),
+    64: np.dtype([("begin", "<u8"), ("end", "<u8"), ("n_children", "<u8"), ("code", "<u8"), ("level", "<u8"),
+                  ("props", "<f8", (4,)), ("dim", "<f8"), ("delta", "<f8")]),
+}
+
+# Every symbol declared in include/rakau_b200.h (checked by tests/test_capi_symbols.py).
+SYMBOLS = [
+    "rk_device_count", "rk_min_size", "rk_tree_create", "rk_tree_destroy", "rk_last_error", "rk_create_error",
+    "rk_tree_set_stream", "rk_tree_synchronize", "rk_tree_build", "rk_tree_update_positions",
+    "rk_tree_update_masses", "rk_tree_clear", "rk_tree_nparts", "rk_tree_nnodes", "rk_tree_ncrit",
+    "rk_tree_box_size", "rk_tree_get_parts", "rk_tree_get_codes", "rk_tree_get_perm", "rk_tree_get_nodes",
+    "rk_tree_get_crit", "rk_tree_acc_pot", "rk_tree_acc_pot_range", "rk_tree_get_group_costs", "rk_tree_exact",
+    "rk_traverse_external_tree",
+]
+
+
+class BuildInfo(C.Structure):
+    _fields_ = [("box_size", C.c_double), ("n_nodes", C.c_uint64), ("n_crit", C.c_uint64),
+                ("max_group", C.c_uint64), ("sort_passes", C.c_uint32), ("ms_total", C.c_float),
+                ("ms_encode", C.c_float), ("ms_sort", C.c_float), ("ms_permute", C.c_float),
+                ("ms_topology", C.c_float), ("ms_props", C.c_float)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class EvalInfo(C.Structure):
+    _fields_ = [("mac_tests", C.c_uint64), ("accepted", C.c_uint64), ("p2p_pairs", C.c_uint64),
+                ("self_pairs", C.c_uint64), ("interactions", C.c_uint64), ("n_groups", C.c_uint64),
+                ("kernel_launches", C.c_uint32), ("ms_kernel", C.c_float), ("ms_total", C.c_float)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class RakauError(Exception):
+    """status: 1 invalid_argument, 2 domain_error, 3 overflow_error, 4 runtime_error, 5 bad_alloc."""
+
+    def __init__(self, status, msg):
+        super().__init__(msg)
+        self.status = status
+
+
+def lib():
+    """Load librakau_b200.so. Raises if it has not been built — there is no fallback path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `make` or __graft_entry__.build(); "
+                           "rakau_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, dbl, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_int
+    L.rk_device_count.restype = C.c_uint
+    L.rk_min_size.restype = C.c_uint
+    L.rk_tree_create.restype = vp
+    L.rk_tree_create.argtypes = [i32, i32, i32]
+    L.rk_tree_destroy.argtypes = [vp]
+    L.rk_last_error.restype = C.c_char_p
+    L.rk_last_error.argtypes = [vp]
+    L.rk_create_error.restype = C.c_char_p
+    L.rk_tree_set_stream.argtypes = [vp, vp]
+    L.rk_tree_synchronize.argtypes = [vp]
+    L.rk_tree_build.argtypes = [vp, vp, vp, vp, vp, sz, i32, dbl, i32, sz, sz, C.POINTER(BuildInfo)]
+    L.rk_tree_update_positions.argtypes = [vp, vp, vp, vp, i32, C.POINTER(BuildInfo)]
+    L.rk_tree_update_masses.argtypes = [vp, vp, i32]
+    L.rk_tree_clear.argtypes = [vp]
+    for f in ("rk_tree_nparts", "rk_tree_nnodes", "rk_tree_ncrit"):
+        getattr(L, f).restype = sz
+        getattr(L, f).argtypes = [vp]
+    L.rk_tree_box_size.restype = dbl
+    L.rk_tree_box_size.argtypes = [vp]
+    L.rk_tree_get_parts.argtypes = [vp, vp, vp, vp, vp]
+    L.rk_tree_get_codes.argtypes = [vp, vp]
+    L.rk_tree_get_perm.argtypes = [vp, i32, vp]
+    L.rk_tree_get_nodes.argtypes = [vp, vp]
+    L.rk_tree_get_crit.argtypes = [vp, vp]
+    L.rk_tree_get_group_costs.argtypes = [vp, vp]
+    L.rk_tree_acc_pot.argtypes = [vp, i32, i32, dbl, dbl, dbl, vp, sz, C.POINTER(vp), i32, C.POINTER(EvalInfo)]
+    L.rk_tree_acc_pot_range.argtypes = [vp, i32, i32, dbl, dbl, dbl, sz, sz, C.POINTER(vp), i32,
+                                        C.POINTER(EvalInfo)]
+    L.rk_tree_exact.argtypes = [vp, sz, i32, dbl, dbl, vp]
+    L.rk_traverse_external_tree.argtypes = [i32, i32, i32, C.POINTER(vp), vp, sz, vp, sz, C.POINTER(vp), vp, sz,
+                                            dbl, dbl, dbl, i32, sz, C.POINTER(EvalInfo), C.c_char_p, sz]
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    """Host numpy array, integer device pointer, or None -> c_void_p."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Octree:
+    """Device-resident octree: mirrors the calls rakau::octree<F, MAC> makes into the C ABI."""
+
+    def __init__(self, fp=32, mac="bh", device=0):
+        self.fp = fp
+        self.F = FDT[fp]
+        self.L = lib()
+        self.h = self.L.rk_tree_create(fp, 0 if mac == "bh" else 1, device)
+        if not self.h:
+            raise RuntimeError(self.L.rk_create_error().decode())
+        self.build_info = BuildInfo()
+        self.eval_info = EvalInfo()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rk_tree_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise RakauError(rc, self.L.rk_last_error(self.h).decode())
+
+    def _prep(self, a, where):
+        if where == RK_HOST and a is not None:
+            return np.ascontiguousarray(a, dtype=self.F)
+        return a
+
+    def set_stream(self, stream_ptr):
+        self._check(self.L.rk_tree_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        self._check(self.L.rk_tree_synchronize(self.h))
+
+    def build(self, x, y, z, m, box_size=0.0, max_leaf_n=16, ncrit=128, where=RK_HOST, n=None):
+        arrs = [self._prep(a, where) for a in (x, y, z, m)]
+        if n is None:
+            n = arrs[0].size if where == RK_HOST else arrs[0].numel()
+        deduce = 1 if not box_size else 0
+        self._keep = arrs
+        self._check(self.L.rk_tree_build(self.h, *[_ptr(a) for a in arrs], n, where, float(box_size or 0.0), deduce,
+                                         max_leaf_n, ncrit, C.byref(self.build_info)))
+        return self.build_info
+
+    def update_positions(self, x=None, y=None, z=None, where=RK_HOST):
+        arrs = [self._prep(a, where) for a in (x, y, z)]
+        self._check(self.L.rk_tree_update_positions(self.h, *[_ptr(a) for a in arrs], where,
+                                                    C.byref(self.build_info)))
+        return self.build_info
+
+    def update_masses(self, m, where=RK_HOST):
+        m = self._prep(m, where)
+        self._check(self.L.rk_tree_update_masses(self.h, _ptr(m), where))
+
+    @property
+    def nparts(self):
+        return self.L.rk_tree_nparts(self.h)
+
+    @property
+    def nnodes(self):
+        return self.L.rk_tree_nnodes(self.h)
+
+    @property
+    def ncrit_nodes(self):
+        return self.L.rk_tree_ncrit(self.h)
+
+    @property
+    def box_size(self):
+        return self.L.rk_tree_box_size(self.h)
+
+    def parts(self):
+        out = [np.empty(self.nparts, dtype=self.F) for _ in range(4)]
+        self._check(self.L.rk_tree_get_parts(self.h, *[_ptr(a) for a in out]))
+        return out
+
+    def codes(self):
+        out = np.empty(self.nparts, dtype=np.uint64)
+        self._check(self.L.rk_tree_get_codes(self.h, _ptr(out)))
+        return out
+
+    def perm(self, which=RK_PERM):
+        out = np.empty(self.nparts, dtype=np.uint64)
+        self._check(self.L.rk_tree_get_perm(self.h, which, _ptr(out)))
+        return out
+
+    def nodes(self):
+        out = np.empty(self.nnodes, dtype=NODE_DTYPE[self.fp])
+        self._check(self.L.rk_tree_get_nodes(self.h, _ptr(out)))
+        return out
+
+    def crit(self):
+        out = np.empty((self.ncrit_nodes, 3), dtype=np.uint64)
+        self._check(self.L.rk_tree_get_crit(self.h, _ptr(out)))
+        return out
+
+    def group_costs(self):
+        out = np.empty(self.ncrit_nodes, dtype=np.uint64)
+        self._check(self.L.rk_tree_get_group_costs(self.h, _ptr(out)))
+        return out
+
+    def acc_pot(self, Q, theta, G=1.0, eps=0.0, ordered=False, split=None, out=None, where=RK_HOST,
+                crit_range=None):
+        """Q: 0 accs, 1 pots, 2 accs+pots. Returns the list of output arrays (host numpy unless `out` given)."""
+        nres = {0: 3, 1: 1, 2: 4}[Q]
+        if out is None:
+            assert where == RK_HOST
+            out = [np.zeros(self.nparts, dtype=self.F) for _ in range(nres)]
+        ptrs = (C.c_void_p * 4)(*([_ptr(a) for a in out] + [None] * (4 - nres)))
+        if crit_range is not None:
+            rc = self.L.rk_tree_acc_pot_range(self.h, Q, int(ordered), float(theta), float(G), float(eps),
+                                              crit_range[0], crit_range[1], ptrs, where, C.byref(self.eval_info))
+        else:
+            sp = None if split is None else np.ascontiguousarray(split, dtype=np.float64)
+            rc = self.L.rk_tree_acc_pot(self.h, Q, int(ordered), float(theta), float(G), float(eps), _ptr(sp),
+                                        0 if sp is None else sp.size, ptrs, where, C.byref(self.eval_info))
+        self._check(rc)
+        return out
+
+    def exact(self, idx, G=1.0, eps=0.0, ordered=False):
+        out = np.zeros(4, dtype=np.float64)
+        self._check(self.L.rk_tree_exact(self.h, idx, int(ordered), float(G), float(eps), _ptr(out)))
+        return out
+
+
+def device_count():
+    return lib().rk_device_count()

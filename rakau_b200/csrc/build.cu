@@ -1,0 +1,901 @@
+// build.cu — particle packing, box deduction, Morton encoding, permutation and the non-recursive octree
+// build for sm_100a. All kernels here are HBM/L2-bound integer or byte work: coalesced, one pass each.
+//
+// Reference functions replaced (include/rakau/tree.hpp):
+//   determine_box_size 1278-1319, disc_single_coord 381-429, morton_encoder 222-242 (libmorton sLUT),
+//   apply_isort 484-507, perm_to_inv_perm 1248-1262, build_tree 932-1111 (+ build_tree_ser_impl 724-833),
+//   compute_node_properties 1116-1237, get_node_centre 450-482.
+//
+// Tree build formulation (validated against the recursive reference semantics by tests/build_model.py):
+// with sorted codes c[i], let delta(i) = #leading 3-bit digits shared by c[i-1], c[i] (delta(0) = -1) and
+// W_w(i) = deepest level at which the cell containing i holds more than w particles (-1 if none)
+//        = max over j in [i, i+w], w <= j < N, of shared_digits(c[j-w], c[j]).
+// Leaf level D(i) = min(W_maxleaf(i)+1, 21); critical level Lc(i) = min(W_max(ncrit,maxleaf)(i)+1, 21).
+// The nodes that begin at particle i are exactly the levels delta(i)+1 .. D(i); DFS pre-order is
+// (begin asc, level asc); the device keeps nodes level-major (BFS) so children are contiguous.
+
+#include "common.cuh"
+#include "scan.cuh"
+
+#include <cmath>
+#include <type_traits>
+
+namespace rk
+{
+
+namespace
+{
+
+// ---------------------------------------------------------------------------------------------------
+// pack / unpack / abs-max
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 abs_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+__device__ __forceinline__ u64 abs_bits(double v)
+{
+    return static_cast<u64>(__double_as_longlong(v)) & 0x7fffffffffffffffull;
+}
+
+__device__ __forceinline__ void block_max_to_global(u64 v, u64 *out)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    if ((threadIdx.x & 31) == 0 && v) {
+        atomicMax(out, v);
+    }
+}
+
+// x,y,z,m SoA -> packed vec4; max |coord| as an unsigned bit pattern (non-negative IEEE values order like
+// unsigned integers; Inf/NaN patterns sort above every finite value, which is how non-finite input is found).
+template <typename F>
+__global__ void __launch_bounds__(256) pack_absmax_kernel(const F *__restrict__ x, const F *__restrict__ y,
+                                                          const F *__restrict__ z, const F *__restrict__ m,
+                                                          vec4<F> *__restrict__ out, size_t n, u64 *__restrict__ absmax)
+{
+    u64 mx = 0;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const F a = x[i], b = y[i], c = z[i];
+        out[i] = make_vec4<F>(a, b, c, m[i]);
+        const u64 ba = abs_bits(a), bb = abs_bits(b), bc = abs_bits(c);
+        mx = ba > mx ? ba : mx;
+        mx = bb > mx ? bb : mx;
+        mx = bc > mx ? bc : mx;
+    }
+    block_max_to_global(mx, absmax);
+}
+
+// Overwrite selected components (NULL = keep) of an already packed array and recompute the abs-max.
+template <typename F>
+__global__ void __launch_bounds__(256) set_coords_kernel(vec4<F> *__restrict__ p, const F *__restrict__ x,
+                                                         const F *__restrict__ y, const F *__restrict__ z,
+                                                         const F *__restrict__ m, size_t n, u64 *__restrict__ absmax)
+{
+    u64 mx = 0;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        vec4<F> v = p[i];
+        if (x) {
+            v.x = x[i];
+        }
+        if (y) {
+            v.y = y[i];
+        }
+        if (z) {
+            v.z = z[i];
+        }
+        if (m) {
+            v.w = m[i];
+        }
+        p[i] = v;
+        const u64 ba = abs_bits(v.x), bb = abs_bits(v.y), bc = abs_bits(v.z);
+        mx = ba > mx ? ba : mx;
+        mx = bb > mx ? bb : mx;
+        mx = bc > mx ? bc : mx;
+    }
+    if (absmax) {
+        block_max_to_global(mx, absmax);
+    }
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256) unpack_kernel(const vec4<F> *__restrict__ in, F *__restrict__ x, F *__restrict__ y,
+                                                     F *__restrict__ z, F *__restrict__ m, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        const vec4<F> v = in[i];
+        if (x) {
+            x[i] = v.x;
+        }
+        if (y) {
+            y[i] = v.y;
+        }
+        if (z) {
+            z[i] = v.z;
+        }
+        if (m) {
+            m[i] = v.w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// discretise + Morton encode (bit-exact with disc_single_coord + m3D_e_sLUT)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 spread3(u64 v)
+{
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+__host__ __device__ inline u64 compact3(u64 v)
+{
+    v &= 0x1249249249249249ull;
+    v = (v ^ (v >> 2)) & 0x10c30c30c30c30c3ull;
+    v = (v ^ (v >> 4)) & 0x100f00f00f00f00full;
+    v = (v ^ (v >> 8)) & 0x1f0000ff0000ffull;
+    v = (v ^ (v >> 16)) & 0x1f00000000ffffull;
+    v = (v ^ (v >> 32)) & 0x1fffffull;
+    return v;
+}
+
+// Returns 0 on success, else the error class (1 non-finite, 2 fp out of bounds, 3 int out of bounds).
+template <typename F>
+__device__ __forceinline__ u32 disc_coord(F x, F inv_box, u64 &out)
+{
+    const F factor = F(2097152); // 2^21
+    F tmp = rn_fma(x, inv_box, F(0.5));
+    tmp = rn_mul(tmp, factor);
+    if (!isfinite(tmp)) {
+        return 1;
+    }
+    if (tmp < F(0) || tmp >= factor) {
+        return 2;
+    }
+    out = static_cast<u64>(tmp); // truncation, value in [0, 2^21)
+    return out >= 2097152ull ? 3u : 0u;
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+    encode_kernel(const vec4<F> *__restrict__ p, u64 *__restrict__ codes, size_t n, F inv_box, u64 *__restrict__ err)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const vec4<F> v = p[i];
+    u64 dx = 0, dy = 0, dz = 0;
+    u32 e = disc_coord(v.x, inv_box, dx), dim = 0;
+    if (!e) {
+        e = disc_coord(v.y, inv_box, dy);
+        dim = 1;
+    }
+    if (!e) {
+        e = disc_coord(v.z, inv_box, dz);
+        dim = 2;
+    }
+    if (e) {
+        // first offending particle wins: key = index << 8 | dim << 4 | class
+        atomicMin(err, (static_cast<u64>(i) << 8) | (dim << 4) | e);
+        codes[i] = 0;
+        return;
+    }
+    codes[i] = spread3(dx) | (spread3(dy) << 1) | (spread3(dz) << 2);
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+    gather_kernel(const vec4<F> *__restrict__ pin, const u32 *__restrict__ idx, vec4<F> *__restrict__ pout, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        pout[i] = pin[idx[i]];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    perm_first_kernel(const u32 *__restrict__ last_perm, u32 *__restrict__ perm, u32 *__restrict__ inv_perm, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        const u32 p = last_perm[i];
+        perm[i] = p;
+        inv_perm[p] = static_cast<u32>(i);
+    }
+}
+
+// apply_isort(m_perm, m_last_perm) + perm_to_inv_perm, tree.hpp:3725-3732.
+__global__ void __launch_bounds__(256)
+    perm_compose_kernel(const u32 *__restrict__ old_perm, const u32 *__restrict__ last_perm, u32 *__restrict__ new_perm,
+                        u32 *__restrict__ inv_perm, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        const u32 p = old_perm[last_perm[i]];
+        new_perm[i] = p;
+        inv_perm[p] = static_cast<u32>(i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// topology
+// ---------------------------------------------------------------------------------------------------
+// delta(i) and the two window arrays P'_w(j) = shared_digits(c[j-w], c[j]) (w <= j < n), else -1.
+__global__ void __launch_bounds__(256) delta_window_kernel(const u64 *__restrict__ codes, size_t n, size_t w1, size_t w2,
+                                                           i8 *__restrict__ delta, i8 *__restrict__ p1,
+                                                           i8 *__restrict__ p2)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const u64 c = codes[i];
+    delta[i] = i ? static_cast<i8>(shared_digits(codes[i - 1], c)) : i8(-1);
+    p1[i] = (i >= w1) ? static_cast<i8>(shared_digits(codes[i - w1], c)) : i8(-1);
+    if (p2) {
+        p2[i] = (i >= w2) ? static_cast<i8>(shared_digits(codes[i - w2], c)) : i8(-1);
+    }
+}
+
+// out[j] = max(in[j], in[j + step]) (missing = -1). 4 bytes per thread.
+__global__ void __launch_bounds__(256) window_double_kernel(const i8 *__restrict__ in, i8 *__restrict__ out, size_t n,
+                                                            size_t step)
+{
+    const size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (j >= n) {
+        return;
+    }
+    const i8 a = in[j];
+    const i8 b = (j + step < n) ? in[j + step] : i8(-1);
+    out[j] = a > b ? a : b;
+}
+
+// lvl[i] = min(21, 1 + max(A[i], A[i + off])) where A holds window maxima of width 2^K and off = w+1-2^K.
+__global__ void __launch_bounds__(256) window_final_kernel(const i8 *__restrict__ A, i8 *__restrict__ lvl, size_t n,
+                                                           size_t off)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const i8 a = A[i];
+    const i8 b = (i + off < n) ? A[i + off] : i8(-1);
+    const int w = a > b ? a : b;
+    lvl[i] = static_cast<i8>(w + 1 > CBITS ? CBITS : w + 1);
+}
+
+__global__ void __launch_bounds__(256) fill_i8_kernel(i8 *p, size_t n, i8 v)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        p[i] = v;
+    }
+}
+
+// Per tile of TOPO_TILE particles: number of nodes beginning in the tile at each level (rows 0..21) and the
+// number of critical nodes beginning in the tile (row 22). tilecnt is row-major [NLEVELS+1][ntiles].
+__global__ void __launch_bounds__(TOPO_TILE)
+    topo_count_kernel(const i8 *__restrict__ delta, const i8 *__restrict__ lvl_leaf, const i8 *__restrict__ lvl_crit,
+                      size_t n, u32 ntiles, u32 *__restrict__ tilecnt)
+{
+    __shared__ u32 cnt[NLEVELS + 1];
+    if (threadIdx.x < NLEVELS + 1) {
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const size_t i = size_t(blockIdx.x) * TOPO_TILE + threadIdx.x;
+    const bool valid = i < n;
+    const int lo = valid ? delta[i] + 1 : 64, hi = valid ? lvl_leaf[i] : -1;
+    const bool critb = valid && (lo <= lvl_crit[i]);
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int l = 0; l < NLEVELS; ++l) {
+        const u32 b = __ballot_sync(0xffffffffu, lo <= l && l <= hi);
+        if (lane == 0 && b) {
+            atomicAdd(&cnt[l], __popc(b));
+        }
+    }
+    {
+        const u32 b = __ballot_sync(0xffffffffu, critb);
+        if (lane == 0 && b) {
+            atomicAdd(&cnt[NLEVELS], __popc(b));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NLEVELS + 1) {
+        tilecnt[size_t(threadIdx.x) * ntiles + blockIdx.x] = cnt[threadIdx.x];
+    }
+}
+
+// Emits the nodes that begin in this tile (BFS positions from the scanned tile counts) and the critical
+// nodes. nodeB.y (end) and the child count are filled by topo_finalize_kernel.
+__global__ void __launch_bounds__(TOPO_TILE)
+    topo_emit_kernel(const i8 *__restrict__ delta, const i8 *__restrict__ lvl_leaf, const i8 *__restrict__ lvl_crit,
+                     size_t n, u32 ntiles, const u32 *__restrict__ tilecnt /* scanned */, level_table lt,
+                     uint4 *__restrict__ nodeB, u32 *__restrict__ node_dfs, u32 *__restrict__ dfsbase,
+                     u32 *__restrict__ crit_node, u32 *__restrict__ crit_begin, u32 n_nodes, u32 n_crit)
+{
+    constexpr int NW = TOPO_TILE / 32;
+    __shared__ u32 wc[NLEVELS + 1][NW];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t i = size_t(blockIdx.x) * TOPO_TILE + threadIdx.x;
+    const bool valid = i < n;
+    const int lo = valid ? delta[i] + 1 : 64, hi = valid ? lvl_leaf[i] : -1;
+    const int lc = valid ? lvl_crit[i] : -1;
+    const bool critb = valid && (lo <= lc);
+    const u32 ltm = lanemask_lt();
+#pragma unroll
+    for (int l = 0; l < NLEVELS; ++l) {
+        const u32 b = __ballot_sync(0xffffffffu, lo <= l && l <= hi);
+        if (lane == 0) {
+            wc[l][w] = __popc(b);
+        }
+    }
+    {
+        const u32 b = __ballot_sync(0xffffffffu, critb);
+        if (lane == 0) {
+            wc[NLEVELS][w] = __popc(b);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NLEVELS + 1) {
+        const int l = threadIdx.x;
+        u32 run = tilecnt[size_t(l) * ntiles + blockIdx.x] + (l < NLEVELS ? lt.base[l] : 0u);
+        for (int k = 0; k < NW; ++k) {
+            const u32 c = wc[l][k];
+            wc[l][k] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // DFS base of particle i = number of nodes beginning at particles < i = sum over levels of the ranks.
+    u32 dfsb = 0;
+#pragma unroll
+    for (int l = 0; l < NLEVELS; ++l) {
+        const u32 b = __ballot_sync(0xffffffffu, lo <= l && l <= hi);
+        dfsb += wc[l][w] - lt.base[l] + __popc(b & ltm);
+    }
+    if (valid) {
+        dfsbase[i] = dfsb;
+        if (i == n - 1) {
+            dfsbase[n] = n_nodes;
+        }
+    }
+    u32 crit_rank = 0;
+    {
+        const u32 b = __ballot_sync(0xffffffffu, critb);
+        crit_rank = wc[NLEVELS][w] + __popc(b & ltm);
+    }
+    // Emit. rank at level l+1 is needed as the first child of the node at level l.
+    u32 prev_rank = 0;
+    bool prev_pred = false;
+#pragma unroll
+    for (int l = 0; l <= NLEVELS; ++l) {
+        bool pred = false;
+        u32 r = 0;
+        if (l < NLEVELS) {
+            pred = lo <= l && l <= hi;
+            const u32 b = __ballot_sync(0xffffffffu, pred);
+            r = wc[l][w] + __popc(b & ltm);
+        }
+        if (prev_pred) {
+            // node (i, l-1): begin, end (later), first child, level
+            nodeB[prev_rank] = make_uint4(static_cast<u32>(i), 0u, pred ? r : 0u, static_cast<u32>(l - 1) << 8);
+            node_dfs[prev_rank] = dfsb + static_cast<u32>(l - 1 - lo);
+            if (critb && lc == l - 1) {
+                crit_node[crit_rank] = prev_rank;
+                crit_begin[crit_rank] = static_cast<u32>(i);
+            }
+        }
+        prev_pred = pred;
+        prev_rank = r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        crit_begin[n_crit] = static_cast<u32>(n);
+    }
+}
+
+// Per node: end of its particle range (galloping + binary search on the sorted codes), number of children
+// (children are contiguous in BFS order), number of descendants (the reference's n_children).
+__global__ void __launch_bounds__(256)
+    topo_finalize_kernel(const u64 *__restrict__ codes, size_t n, uint4 *__restrict__ nodeB,
+                         const u32 *__restrict__ node_dfs, const u32 *__restrict__ dfsbase, u32 *__restrict__ node_ndesc,
+                         level_table lt, u32 n_nodes)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_nodes) {
+        return;
+    }
+    uint4 nb = nodeB[k];
+    const u32 b = nb.x, level = nb.w >> 8;
+    u32 e;
+    if (level == 0) {
+        e = static_cast<u32>(n);
+    } else {
+        const int sh = 3 * (CBITS - static_cast<int>(level));
+        const u64 pre = codes[b] >> sh;
+        // gallop: largest known index inside the cell is lo; hi is the first index known outside (or n).
+        size_t lo = b, step = 1, hi = n;
+        while (lo + step < n) {
+            if ((codes[lo + step] >> sh) == pre) {
+                lo += step;
+                step <<= 1;
+            } else {
+                hi = lo + step;
+                break;
+            }
+        }
+        // invariant: cell contains lo, does not contain hi (or hi == n)
+        while (hi - lo > 1) {
+            const size_t mid = lo + (hi - lo) / 2;
+            if ((codes[mid] >> sh) == pre) {
+                lo = mid;
+            } else {
+                hi = mid;
+            }
+        }
+        e = static_cast<u32>(hi);
+    }
+    nb.y = e;
+    nodeB[k] = nb;
+    node_ndesc[k] = dfsbase[e] - node_dfs[k] - 1u;
+}
+
+// Second finalize pass (needs every node's end): child count.
+__global__ void __launch_bounds__(256)
+    topo_children_kernel(uint4 *__restrict__ nodeB, level_table lt, u32 n_nodes)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_nodes) {
+        return;
+    }
+    uint4 nb = nodeB[k];
+    const u32 level = nb.w >> 8;
+    u32 nch = 0;
+    if (nb.z) {
+        const u32 fc = nb.z, lim = lt.base[level + 2]; // end of level+1 segment
+#pragma unroll
+        for (u32 t = 0; t < 8; ++t) {
+            if (fc + t < lim && nodeB[fc + t].x < nb.y) {
+                ++nch;
+            }
+        }
+    }
+    nb.w = (level << 8) | nch;
+    nodeB[k] = nb;
+}
+
+__global__ void __launch_bounds__(256) max_group_kernel(const u32 *__restrict__ crit_begin, u32 n_crit, u32 *__restrict__ out)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 v = 0;
+    if (j < n_crit) {
+        v = crit_begin[j + 1] - crit_begin[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u32 t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    if ((threadIdx.x & 31) == 0 && v) {
+        atomicMax(out, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// node properties
+// ---------------------------------------------------------------------------------------------------
+struct dsum4 {
+    double m, x, y, z;
+};
+__device__ __forceinline__ void dsum_add_particle(dsum4 &s, double px, double py, double pz, double pm)
+{
+    s.m += pm;
+    s.x = fma(pm, px, s.x);
+    s.y = fma(pm, py, s.y);
+    s.z = fma(pm, pz, s.z);
+}
+__device__ __forceinline__ void dsum_warp_reduce(dsum4 &s)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s.m += __shfl_xor_sync(0xffffffffu, s.m, o);
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
+    }
+}
+
+// One warp per chunk of PROPS_CHUNK particles: (sum m, sum m*x, sum m*y, sum m*z) in double.
+template <typename F>
+__global__ void __launch_bounds__(256)
+    chunk_sums_kernel(const vec4<F> *__restrict__ p, size_t n, u32 nchunks, double *__restrict__ out)
+{
+    const u32 c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= nchunks) {
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    dsum4 s{0, 0, 0, 0};
+    const size_t b = size_t(c) * PROPS_CHUNK;
+#pragma unroll
+    for (int j = 0; j < PROPS_CHUNK / 32; ++j) {
+        const size_t i = b + size_t(j) * 32 + lane;
+        if (i < n) {
+            const vec4<F> v = p[i];
+            dsum_add_particle(s, v.x, v.y, v.z, v.w);
+        }
+    }
+    dsum_warp_reduce(s);
+    if (lane == 0) {
+        out[size_t(c) * 4 + 0] = s.m;
+        out[size_t(c) * 4 + 1] = s.x;
+        out[size_t(c) * 4 + 2] = s.y;
+        out[size_t(c) * 4 + 3] = s.z;
+    }
+}
+
+template <typename F>
+struct level_dims {
+    F dim[NLEVELS];  // box / 2^level  (get_node_dim, tree.hpp:443-448)
+    F cell;          // box * (1 / 2^21)
+    F half_box;      // box * (1/2)
+};
+
+// get_node_centre, tree.hpp:450-482, with explicitly rounded operations.
+template <typename F>
+__device__ __forceinline__ void node_centre_dev(F out[3], u64 first_code, u32 level, const level_dims<F> &ld)
+{
+    const int sh = 3 * (CBITS - static_cast<int>(level));
+    const u64 cell_code = (level == 0) ? 0ull : ((first_code >> sh) << sh);
+    const F half_dim = rn_mul(ld.dim[level], F(0.5));
+    const F off = rn_sub(half_dim, ld.half_box);
+    const u64 d[3] = {compact3(cell_code), compact3(cell_code >> 1), compact3(cell_code >> 2)};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        out[j] = rn_fma(static_cast<F>(d[j]), ld.cell, off);
+    }
+}
+
+// One warp per node. The reduction shape (lane-strided partial sums over head particles, whole chunks and
+// tail particles, then a fixed shuffle tree) depends only on the node's range, never on the mass values,
+// so scaling all masses by a power of two scales every partial exactly (reference test update_masses.cpp:56-68).
+template <typename F>
+__global__ void __launch_bounds__(256)
+    node_props_kernel(const vec4<F> *__restrict__ p, const u64 *__restrict__ codes, const double *__restrict__ chunks,
+                      const uint4 *__restrict__ nodeB, vec4<F> *__restrict__ nodeA, F *__restrict__ node_delta,
+                      u32 n_nodes, int mac, level_dims<F> ld, u64 *__restrict__ err)
+{
+    const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_nodes) {
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const uint4 nb = nodeB[k];
+    const u32 b = nb.x, e = nb.y, level = nb.w >> 8;
+    dsum4 s{0, 0, 0, 0};
+    const u32 cb = (b + PROPS_CHUNK - 1) / PROPS_CHUNK, ce = e / PROPS_CHUNK;
+    if (cb >= ce) {
+        for (u32 i = b + lane; i < e; i += 32) {
+            const vec4<F> v = p[i];
+            dsum_add_particle(s, v.x, v.y, v.z, v.w);
+        }
+    } else {
+        for (u32 i = b + lane; i < cb * PROPS_CHUNK; i += 32) {
+            const vec4<F> v = p[i];
+            dsum_add_particle(s, v.x, v.y, v.z, v.w);
+        }
+        for (u32 c = cb + lane; c < ce; c += 32) {
+            const double4 cs = *reinterpret_cast<const double4 *>(chunks + size_t(c) * 4);
+            s.m += cs.x;
+            s.x += cs.y;
+            s.y += cs.z;
+            s.z += cs.w;
+        }
+        for (u32 i = ce * PROPS_CHUNK + lane; i < e; i += 32) {
+            const vec4<F> v = p[i];
+            dsum_add_particle(s, v.x, v.y, v.z, v.w);
+        }
+    }
+    dsum_warp_reduce(s);
+    if (lane != 0) {
+        return;
+    }
+    const F tot = static_cast<F>(s.m);
+    F com[3], geo[3] = {F(0), F(0), F(0)};
+    const u64 c0 = codes[b];
+    if (mac == 1) {
+        node_centre_dev(geo, c0, level, ld);
+    }
+    if (tot == F(0)) {
+        if (mac == 1) {
+            com[0] = geo[0];
+            com[1] = geo[1];
+            com[2] = geo[2];
+        } else {
+            node_centre_dev(com, c0, level, ld);
+        }
+    } else {
+        const double inv = 1.0 / s.m;
+        com[0] = static_cast<F>(s.x * inv);
+        com[1] = static_cast<F>(s.y * inv);
+        com[2] = static_cast<F>(s.z * inv);
+    }
+    u32 ecode = 0;
+    if (!isfinite(com[0]) || !isfinite(com[1]) || !isfinite(com[2])) {
+        ecode = 5;
+    } else if (!isfinite(tot)) {
+        ecode = 6;
+    }
+    nodeA[k] = make_vec4<F>(com[0], com[1], com[2], tot);
+    if (mac == 1) {
+        const F d0 = rn_sub(com[0], geo[0]), d1 = rn_sub(com[1], geo[1]), d2 = rn_sub(com[2], geo[2]);
+        F dd = rn_mul(d0, d0);
+        dd = rn_fma(d1, d1, dd);
+        dd = rn_fma(d2, d2, dd);
+        const F dl = rn_sqrt(dd);
+        node_delta[k] = dl;
+        if (!ecode && !isfinite(dl)) {
+            ecode = 7;
+        }
+    }
+    if (ecode) {
+        atomicMin(err, (static_cast<u64>(k) << 8) | ecode);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// export to the reference's host layout
+// ---------------------------------------------------------------------------------------------------
+template <typename F>
+struct host_node {
+    u64 begin, end, n_children, code, level;
+    F props[4], dim, delta;
+};
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+    export_nodes_kernel(const u64 *__restrict__ codes, const uint4 *__restrict__ nodeB, const vec4<F> *__restrict__ nodeA,
+                        const F *__restrict__ node_delta, const u32 *__restrict__ node_dfs,
+                        const u32 *__restrict__ node_ndesc, u32 n_nodes, int mac, level_dims<F> ld,
+                        host_node<F> *__restrict__ out)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_nodes) {
+        return;
+    }
+    const uint4 nb = nodeB[k];
+    const vec4<F> a = nodeA[k];
+    const u32 level = nb.w >> 8;
+    host_node<F> h;
+    h.begin = nb.x;
+    h.end = nb.y;
+    h.n_children = node_ndesc[k];
+    h.level = level;
+    h.code = (1ull << (3 * level)) | (level ? (codes[nb.x] >> (3 * (CBITS - static_cast<int>(level)))) : 0ull);
+    h.props[0] = a.x;
+    h.props[1] = a.y;
+    h.props[2] = a.z;
+    h.props[3] = a.w;
+    if (mac == 0) {
+        h.dim = rn_mul(ld.dim[level], ld.dim[level]); // dim2 = node_dim * node_dim, tree.hpp:1212
+        h.delta = F(0);
+    } else {
+        h.dim = ld.dim[level];
+        h.delta = node_delta[k];
+    }
+    out[node_dfs[k]] = h;
+}
+
+__global__ void __launch_bounds__(256)
+    export_crit_kernel(const u64 *__restrict__ codes, const uint4 *__restrict__ nodeB, const u32 *__restrict__ crit_node,
+                       const u32 *__restrict__ crit_begin, u32 n_crit, u64 *__restrict__ out)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_crit) {
+        return;
+    }
+    const uint4 nb = nodeB[crit_node[j]];
+    const u32 level = nb.w >> 8;
+    out[3 * size_t(j) + 0]
+        = (1ull << (3 * level)) | (level ? (codes[nb.x] >> (3 * (CBITS - static_cast<int>(level)))) : 0ull);
+    out[3 * size_t(j) + 1] = crit_begin[j];
+    out[3 * size_t(j) + 2] = crit_begin[j + 1];
+}
+
+template <typename F>
+level_dims<F> make_level_dims(F box)
+{
+    level_dims<F> ld;
+    for (int l = 0; l < NLEVELS; ++l) {
+        ld.dim[l] = box / static_cast<F>(u64(1) << l);
+    }
+    ld.cell = box * (F(1) / static_cast<F>(u64(1) << CBITS));
+    ld.half_box = box * (F(1) / F(2));
+    return ld;
+}
+
+// Sliding-window level: lvl[i] = min(21, 1 + max_{j in [i, i+w]} P'(j)); `a` holds P' on entry.
+void window_levels(i8 *a, i8 *bbuf, i8 *lvl, size_t n, size_t w, cudaStream_t st)
+{
+    const unsigned g = div_up(n, 256);
+    if (w >= n) {
+        fill_i8_kernel<<<g, 256, 0, st>>>(lvl, n, i8(0));
+        return;
+    }
+    size_t k = 1;
+    i8 *in = a, *out = bbuf;
+    while (k * 2 <= w + 1) {
+        window_double_kernel<<<g, 256, 0, st>>>(in, out, n, k);
+        i8 *t = in;
+        in = out;
+        out = t;
+        k *= 2;
+    }
+    window_final_kernel<<<g, 256, 0, st>>>(in, lvl, n, w + 1 - k);
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------------
+constexpr unsigned STREAM_GRID = 148 * 8; // grid-stride kernels: a multiple of the SM count
+
+template <typename F>
+void launch_pack_absmax(const F *x, const F *y, const F *z, const F *m, vec4<F> *out, size_t n, u64 *absmax_bits,
+                        cudaStream_t st)
+{
+    if (n) {
+        pack_absmax_kernel<F><<<STREAM_GRID, 256, 0, st>>>(x, y, z, m, out, n, absmax_bits);
+    }
+}
+template <typename F>
+void launch_set_coords(vec4<F> *p, const F *x, const F *y, const F *z, const F *m, size_t n, u64 *absmax_bits,
+                       cudaStream_t st)
+{
+    if (n) {
+        set_coords_kernel<F><<<STREAM_GRID, 256, 0, st>>>(p, x, y, z, m, n, absmax_bits);
+    }
+}
+template <typename F>
+void launch_unpack(const vec4<F> *in, F *x, F *y, F *z, F *m, size_t n, cudaStream_t st)
+{
+    if (n) {
+        unpack_kernel<F><<<div_up(n, 256), 256, 0, st>>>(in, x, y, z, m, n);
+    }
+}
+template <typename F>
+void launch_encode(const vec4<F> *p, u64 *codes, size_t n, F inv_box, dev_error *err, cudaStream_t st)
+{
+    if (n) {
+        encode_kernel<F><<<div_up(n, 256), 256, 0, st>>>(p, codes, n, inv_box, reinterpret_cast<u64 *>(err));
+    }
+}
+template <typename F>
+void launch_gather(const vec4<F> *pin, const u32 *idx, vec4<F> *pout, size_t n, cudaStream_t st)
+{
+    if (n) {
+        gather_kernel<F><<<div_up(n, 256), 256, 0, st>>>(pin, idx, pout, n);
+    }
+}
+void launch_perm_first(const u32 *last_perm, u32 *perm, u32 *inv_perm, size_t n, cudaStream_t st)
+{
+    if (n) {
+        perm_first_kernel<<<div_up(n, 256), 256, 0, st>>>(last_perm, perm, inv_perm, n);
+    }
+}
+void launch_perm_compose(const u32 *old_perm, const u32 *last_perm, u32 *new_perm, u32 *inv_perm, size_t n,
+                         cudaStream_t st)
+{
+    if (n) {
+        perm_compose_kernel<<<div_up(n, 256), 256, 0, st>>>(old_perm, last_perm, new_perm, inv_perm, n);
+    }
+}
+
+template <typename F>
+void topology_count(build_arrays<F> &b, size_t max_leaf_n, size_t ncrit, cudaStream_t st)
+{
+    const size_t n = b.n;
+    const u32 ntiles = div_up(n, TOPO_TILE);
+    b.delta.reserve(n, 1.05);
+    b.lvl_leaf.reserve(n, 1.05);
+    b.lvl_crit.reserve(n, 1.05);
+    b.win_a.reserve(2 * n, 1.05); // two P' arrays
+    b.win_b.reserve(n, 1.05);
+    b.dfsbase.reserve(n + 1, 1.05);
+    b.tilecnt.reserve(size_t(NLEVELS + 1) * ntiles, 1.25);
+    b.rowtot.reserve(NLEVELS + 1);
+    const size_t w1 = max_leaf_n, w2 = ncrit > max_leaf_n ? ncrit : max_leaf_n;
+    i8 *p1 = b.win_a.p, *p2 = (w2 != w1) ? b.win_a.p + n : nullptr;
+    delta_window_kernel<<<div_up(n, 256), 256, 0, st>>>(b.codes, n, w1, w2, b.delta.p, p1, p2);
+    window_levels(p1, b.win_b.p, b.lvl_leaf.p, n, w1, st);
+    if (p2) {
+        window_levels(p2, b.win_b.p, b.lvl_crit.p, n, w2, st);
+    } else {
+        RK_CUDA_CHECK(cudaMemcpyAsync(b.lvl_crit.p, b.lvl_leaf.p, n, cudaMemcpyDeviceToDevice, st));
+    }
+    topo_count_kernel<<<ntiles, TOPO_TILE, 0, st>>>(b.delta.p, b.lvl_leaf.p, b.lvl_crit.p, n, ntiles, b.tilecnt.p);
+    row_scan_kernel<<<NLEVELS + 1, 256, 0, st>>>(b.tilecnt.p, ntiles, b.rowtot.p);
+    RK_CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename F>
+void topology_emit(build_arrays<F> &b, cudaStream_t st)
+{
+    const size_t n = b.n;
+    const u32 ntiles = div_up(n, TOPO_TILE);
+    const u32 M = static_cast<u32>(b.n_nodes), C = static_cast<u32>(b.n_crit);
+    topo_emit_kernel<<<ntiles, TOPO_TILE, 0, st>>>(b.delta.p, b.lvl_leaf.p, b.lvl_crit.p, n, ntiles, b.tilecnt.p,
+                                                   b.levels, b.nodeB.p, b.node_dfs.p, b.dfsbase.p, b.crit_node.p,
+                                                   b.crit_begin.p, M, C);
+    topo_finalize_kernel<<<div_up(M, 256), 256, 0, st>>>(b.codes, n, b.nodeB.p, b.node_dfs.p, b.dfsbase.p,
+                                                         b.node_ndesc.p, b.levels, M);
+    topo_children_kernel<<<div_up(M, 256), 256, 0, st>>>(b.nodeB.p, b.levels, M);
+    RK_CUDA_CHECK(cudaMemsetAsync(b.d_misc.p + 2, 0, sizeof(u32), st));
+    max_group_kernel<<<div_up(C, 256), 256, 0, st>>>(b.crit_begin.p, C, b.d_misc.p + 2);
+    RK_CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename F>
+void node_properties(build_arrays<F> &b, int mac, F box_size, cudaStream_t st)
+{
+    const size_t n = b.n;
+    const u32 M = static_cast<u32>(b.n_nodes);
+    if (!M) {
+        return;
+    }
+    const u32 nchunks = div_up(n, PROPS_CHUNK);
+    b.chunksum.reserve(size_t(nchunks) * 4, 1.05);
+    chunk_sums_kernel<F><<<div_up(size_t(nchunks) * 32, 256), 256, 0, st>>>(b.psorted.p, n, nchunks, b.chunksum.p);
+    node_props_kernel<F><<<div_up(size_t(M) * 32, 256), 256, 0, st>>>(
+        b.psorted.p, b.codes, b.chunksum.p, b.nodeB.p, b.nodeA.p, b.node_delta.p, M, mac, make_level_dims<F>(box_size),
+        reinterpret_cast<u64 *>(b.d_err.p) + 1);
+    RK_CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename F>
+void launch_export_nodes(const build_arrays<F> &b, int mac, F box_size, void *d_out, cudaStream_t st)
+{
+    const u32 M = static_cast<u32>(b.n_nodes);
+    if (M) {
+        export_nodes_kernel<F><<<div_up(M, 256), 256, 0, st>>>(b.codes, b.nodeB.p, b.nodeA.p, b.node_delta.p,
+                                                               b.node_dfs.p, b.node_ndesc.p, M, mac,
+                                                               make_level_dims<F>(box_size),
+                                                               static_cast<host_node<F> *>(d_out));
+    }
+}
+
+void launch_export_crit(const u64 *codes, const uint4 *nodeB, const u32 *crit_node, const u32 *crit_begin, size_t n_crit,
+                        u64 *d_out, cudaStream_t st)
+{
+    if (n_crit) {
+        export_crit_kernel<<<div_up(n_crit, 256), 256, 0, st>>>(codes, nodeB, crit_node, crit_begin,
+                                                                static_cast<u32>(n_crit), d_out);
+    }
+}
+
+#define RK_INSTANTIATE(F)                                                                                              \
+    template void launch_pack_absmax<F>(const F *, const F *, const F *, const F *, vec4<F> *, size_t, u64 *,          \
+                                        cudaStream_t);                                                                 \
+    template void launch_set_coords<F>(vec4<F> *, const F *, const F *, const F *, const F *, size_t, u64 *,           \
+                                       cudaStream_t);                                                                  \
+    template void launch_unpack<F>(const vec4<F> *, F *, F *, F *, F *, size_t, cudaStream_t);                         \
+    template void launch_encode<F>(const vec4<F> *, u64 *, size_t, F, dev_error *, cudaStream_t);                      \
+    template void launch_gather<F>(const vec4<F> *, const u32 *, vec4<F> *, size_t, cudaStream_t);                     \
+    template void topology_count<F>(build_arrays<F> &, size_t, size_t, cudaStream_t);                                  \
+    template void topology_emit<F>(build_arrays<F> &, cudaStream_t);                                                   \
+    template void node_properties<F>(build_arrays<F> &, int, F, cudaStream_t);                                         \
+    template void launch_export_nodes<F>(const build_arrays<F> &, int, F, void *, cudaStream_t);
+
+RK_INSTANTIATE(float)
+RK_INSTANTIATE(double)
+
+} // namespace rk

@@ -1,0 +1,931 @@
+// capi.cu — host side of librakau_b200.so: the device-resident tree object and the extern "C" boundary
+// declared in include/rakau_b200.h. Host logic mirrors the reference's construct_impl (tree.hpp:1329-1487),
+// sync (3678-3743), update_masses_dispatch (3782-3805), acc_pot_dispatch (3293-3334) and acc_pot_impl's
+// argument validation (2857-2868, 3134-3141), including the exception messages its tests look for.
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+
+#include "../../include/rakau_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace rk
+{
+
+struct api_error : std::runtime_error {
+    int status;
+    api_error(int st, const std::string &s) : std::runtime_error(s), status(st) {}
+};
+
+template <typename F>
+struct host_node_t {
+    u64 begin, end, n_children, code, level;
+    F props[4], dim, delta;
+};
+static_assert(sizeof(host_node_t<float>) == sizeof(rk_node_f32), "node layout");
+static_assert(sizeof(host_node_t<double>) == sizeof(rk_node_f64), "node layout");
+
+struct timer_events {
+    cudaEvent_t ev[8] = {};
+    void init()
+    {
+        for (auto &e : ev) {
+            RK_CUDA_CHECK(cudaEventCreate(&e));
+        }
+    }
+    void destroy()
+    {
+        for (auto &e : ev) {
+            if (e) {
+                cudaEventDestroy(e);
+            }
+        }
+    }
+};
+
+template <typename F>
+class tree
+{
+public:
+    tree(int mac, int device) : m_mac(mac), m_device(device)
+    {
+        RK_CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        RK_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        m_sm_count = prop.multiProcessorCount;
+        RK_CUDA_CHECK(cudaStreamCreateWithFlags(&m_own_stream, cudaStreamNonBlocking));
+        m_stream = m_own_stream;
+        m_ev.init();
+        RK_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m_hpin), 64 * sizeof(u64)));
+        m_b.d_err.reserve(2);
+        m_b.d_misc.reserve(8);
+        m_counters.reserve(8);
+        m_work.reserve(4);
+    }
+    ~tree()
+    {
+        cudaSetDevice(m_device);
+        cudaStreamSynchronize(m_stream);
+        m_ev.destroy();
+        if (m_hpin) {
+            cudaFreeHost(m_hpin);
+        }
+        if (m_sc.h_ghist) {
+            cudaFreeHost(m_sc.h_ghist);
+        }
+        if (m_own_stream) {
+            cudaStreamDestroy(m_own_stream);
+        }
+    }
+    void use() const { RK_CUDA_CHECK(cudaSetDevice(m_device)); }
+    void set_stream(void *s) { m_stream = s ? static_cast<cudaStream_t>(s) : m_own_stream; }
+    void synchronize()
+    {
+        use();
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+
+    size_t nparts() const { return m_b.n; }
+    size_t nnodes() const { return m_b.n_nodes; }
+    size_t ncrit_nodes() const { return m_b.n_crit; }
+    double box_size() const { return static_cast<double>(m_box); }
+
+    void clear()
+    {
+        m_b.n = 0;
+        m_b.n_nodes = 0;
+        m_b.n_crit = 0;
+        m_b.codes = nullptr;
+        m_b.last_perm = nullptr;
+        m_box = F(0);
+        m_box_deduced = false;
+        m_max_group = 0;
+        m_costs_valid = false;
+        m_h_crit_begin.clear();
+    }
+
+    // ---- construct_impl, tree.hpp:1329-1487 --------------------------------------------------------------
+    void build(const void *x, const void *y, const void *z, const void *m, size_t n, int where, double box_size,
+               bool deduce, size_t max_leaf_n, size_t ncrit, rk_build_info *info)
+    {
+        use();
+        clear();
+        const F bs = static_cast<F>(box_size);
+        // parameter checks, tree.hpp:1350-1362
+        if (!std::isfinite(bs) || bs < F(0)) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "The box size must be a finite non-negative value, but it is "
+                                                         + std::to_string(bs) + " instead");
+        }
+        if (!max_leaf_n) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "The maximum number of particles per leaf must be nonzero");
+        }
+        if (!ncrit) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT,
+                            "The critical number of particles for the vectorised computation of the "
+                            "potentials/accelerations must be nonzero");
+        }
+        if (n > 0xfffffff0ull) {
+            throw api_error(RK_ERR_OVERFLOW, "The number of particles (" + std::to_string(n)
+                                                 + ") is too large, and it results in an overflow condition");
+        }
+        m_box = bs;
+        m_box_deduced = deduce;
+        m_max_leaf_n = max_leaf_n;
+        m_ncrit = ncrit;
+        m_b.n = n;
+        try {
+            reserve_particles(n);
+            RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[0], m_stream));
+            const F *dx, *dy, *dz, *dm;
+            upload4(x, y, z, m, n, where, dx, dy, dz, dm);
+            reset_flags();
+            launch_pack_absmax<F>(dx, dy, dz, dm, m_b.pin.p, n, reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
+            rebuild(true, info);
+        } catch (...) {
+            clear();
+            throw;
+        }
+    }
+
+    // ---- sync(), tree.hpp:3678-3743 ------------------------------------------------------------------------
+    void update_positions(const void *x, const void *y, const void *z, int where, rk_build_info *info)
+    {
+        use();
+        const size_t n = m_b.n;
+        try {
+            RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[0], m_stream));
+            const F *dx, *dy, *dz, *dm;
+            upload4(x, y, z, nullptr, n, where, dx, dy, dz, dm);
+            reset_flags();
+            // the current Morton order becomes the pre-sort order of the new build
+            std::swap(m_b.pin.p, m_b.psorted.p);
+            std::swap(m_b.pin.cap, m_b.psorted.cap);
+            launch_set_coords<F>(m_b.pin.p, dx, dy, dz, nullptr, n, reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
+            rebuild(false, info);
+        } catch (...) {
+            clear();
+            throw;
+        }
+    }
+
+    // ---- update_masses_dispatch, tree.hpp:3782-3805 --------------------------------------------------------
+    void update_masses(const void *m, int where)
+    {
+        use();
+        const size_t n = m_b.n;
+        try {
+            const F *dx, *dy, *dz, *dm;
+            upload4(nullptr, nullptr, nullptr, m, n, where, dx, dy, dz, dm);
+            reset_flags();
+            launch_set_coords<F>(m_b.psorted.p, nullptr, nullptr, nullptr, dm, n, nullptr, m_stream);
+            node_properties<F>(m_b, m_mac, m_box, m_stream);
+            RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_err.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+            check_props_error(m_hpin[1]);
+            m_costs_valid = false;
+        } catch (...) {
+            clear();
+            throw;
+        }
+    }
+
+    // ---- getters ---------------------------------------------------------------------------------------------
+    void get_parts(void *x, void *y, void *z, void *m)
+    {
+        use();
+        const size_t n = m_b.n;
+        if (!n) {
+            return;
+        }
+        void *outs[4] = {x, y, z, m};
+        F *d[4];
+        for (int j = 0; j < 4; ++j) {
+            m_b.stage[j].reserve(n, 1.05);
+            d[j] = outs[j] ? m_b.stage[j].p : nullptr;
+        }
+        launch_unpack<F>(m_b.psorted.p, d[0], d[1], d[2], d[3], n, m_stream);
+        for (int j = 0; j < 4; ++j) {
+            if (outs[j]) {
+                RK_CUDA_CHECK(cudaMemcpyAsync(outs[j], d[j], n * sizeof(F), cudaMemcpyDeviceToHost, m_stream));
+            }
+        }
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+    void get_codes(uint64_t *codes)
+    {
+        use();
+        if (m_b.n) {
+            RK_CUDA_CHECK(cudaMemcpyAsync(codes, m_b.codes, m_b.n * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        }
+    }
+    void get_perm(int which, uint64_t *out)
+    {
+        use();
+        const size_t n = m_b.n;
+        if (!n) {
+            return;
+        }
+        const u32 *src = which == RK_PERM ? m_b.perm.p : (which == RK_LAST_PERM ? m_b.last_perm : m_b.inv_perm.p);
+        std::vector<u32> tmp(n);
+        RK_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), src, n * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        for (size_t i = 0; i < n; ++i) {
+            out[i] = tmp[i];
+        }
+    }
+    void get_nodes(void *nodes)
+    {
+        use();
+        const size_t M = m_b.n_nodes;
+        if (!M) {
+            return;
+        }
+        dbuf<host_node_t<F>> tmp;
+        tmp.reserve(M);
+        launch_export_nodes<F>(m_b, m_mac, m_box, tmp.p, m_stream);
+        RK_CUDA_CHECK(cudaMemcpyAsync(nodes, tmp.p, M * sizeof(host_node_t<F>), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+    void get_crit(rk_cnode *crit)
+    {
+        use();
+        const size_t C = m_b.n_crit;
+        if (!C) {
+            return;
+        }
+        dbuf<u64> tmp;
+        tmp.reserve(3 * C);
+        launch_export_crit(m_b.codes, m_b.nodeB.p, m_b.crit_node.p, m_b.crit_begin.p, C, tmp.p, m_stream);
+        RK_CUDA_CHECK(cudaMemcpyAsync(crit, tmp.p, 3 * C * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+    void get_group_costs(uint64_t *costs)
+    {
+        use();
+        if (!m_costs_valid) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "No evaluation has been run on this tree yet");
+        }
+        RK_CUDA_CHECK(
+            cudaMemcpyAsync(costs, m_group_cost.p, m_b.n_crit * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+
+    // ---- acc_pot_dispatch (tree.hpp:3293-3334) + acc_pot_impl (2853-3265) ----------------------------------
+    void acc_pot(int Q, bool ordered, double theta_d, double G_d, double eps_d, const double *split, size_t nsplit,
+                 bool ranged, size_t c0, size_t c1, void *const out[4], int where, rk_eval_info *info)
+    {
+        use();
+        if (Q < 0 || Q > 2) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "Invalid value for Q");
+        }
+        const F theta = static_cast<F>(theta_d), G = static_cast<F>(G_d), eps = static_cast<F>(eps_d);
+        if (!std::isfinite(theta) || theta <= F(0)) {
+            throw api_error(RK_ERR_DOMAIN, "The MAC value must be finite and positive, but it is "
+                                               + std::to_string(theta) + " instead");
+        }
+        const F mac_value = (m_mac == RK_MAC_BH) ? F(1) / (theta * theta) : F(1) / theta;
+        if (!std::isfinite(mac_value) || mac_value <= F(0)) {
+            throw api_error(RK_ERR_DOMAIN, "The transformed MAC value must be finite and positive, but it is "
+                                               + std::to_string(mac_value) + " instead");
+        }
+        // compute_eps2 / check_G_const, tree.hpp:3268-3289
+        if (!std::isfinite(eps) || eps < F(0)) {
+            throw api_error(RK_ERR_DOMAIN, "The softening length must be finite and non-negative, but it is "
+                                               + std::to_string(eps) + " instead");
+        }
+        const F eps2 = eps * eps;
+        if (!std::isfinite(eps2) || eps2 < F(0)) {
+            throw api_error(RK_ERR_DOMAIN,
+                            "The square of the softening length must be finite and non-negative, but it is "
+                                + std::to_string(eps2) + " instead");
+        }
+        if (!std::isfinite(G)) {
+            throw api_error(RK_ERR_DOMAIN, "The value of the gravitational constant G must be finite, but it is "
+                                               + std::to_string(G) + " instead");
+        }
+        // split validation, tree.hpp:2857-2868 and 3134-3141. There is no CPU path here: every share runs on
+        // this tree's GPU (documented deviation).
+        for (size_t i = 0; i < nsplit; ++i) {
+            if (!std::isfinite(split[i])) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT, "The 'split' parameter cannot contain non-finite values");
+            }
+        }
+        for (size_t i = 0; i < nsplit; ++i) {
+            if (split[i] < 0.) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT,
+                                "The 'split' parameter must contain only non-negative values");
+            }
+        }
+        if (nsplit && std::all_of(split, split + nsplit, [](double v) { return v == 0.; })) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "The values in the 'split' parameter cannot all be zero");
+        }
+        if (nsplit) {
+            const unsigned ndev = rk_device_count();
+            if (nsplit - 1u > ndev) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT,
+                                "Cannot split the computation of accelerations/potentials: the split vector refers to "
+                                    + std::to_string(nsplit - 1u) + " accelerators, but only " + std::to_string(ndev)
+                                    + " were detected");
+            }
+        }
+        const size_t n = m_b.n, C = m_b.n_crit;
+        if (!ranged) {
+            c0 = 0;
+            c1 = C;
+        }
+        if (c0 > c1 || c1 > C) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "Invalid range of critical nodes");
+        }
+        const int nres = Q == 0 ? 3 : (Q == 1 ? 1 : 4);
+        if (info) {
+            std::memset(info, 0, sizeof(*info));
+        }
+        if (!n || c0 == c1) {
+            return;
+        }
+        for (int j = 0; j < nres; ++j) {
+            if (!out[j]) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT, "Null output pointer");
+            }
+        }
+
+        trav_params<F> p{};
+        p.parts = m_b.psorted.p;
+        p.nodeA = m_b.nodeA.p;
+        p.nodeB = m_b.nodeB.p;
+        p.node_delta = m_b.node_delta.p;
+        p.crit_node = m_b.crit_node.p;
+        p.crit_begin = m_b.crit_begin.p;
+        p.c0 = static_cast<u32>(c0);
+        p.c1 = static_cast<u32>(c1);
+        p.work_counter = m_work.p;
+        for (int l = 0; l < NLEVELS; ++l) {
+            const F nd = m_box / static_cast<F>(u64(1) << l); // get_node_dim, tree.hpp:443-448
+            p.mac_tab[l] = (m_mac == RK_MAC_BH) ? (nd * nd) * mac_value : nd;
+        }
+        p.mac_value = mac_value;
+        p.eps2 = eps2;
+        p.G = G;
+        p.perm = ordered ? m_b.perm.p : nullptr;
+        m_group_cost.reserve(C, 1.1);
+        p.group_cost = m_group_cost.p;
+        p.counters = reinterpret_cast<u64 *>(m_counters.p);
+        u32 tmax = static_cast<u32>((std::min<size_t>(m_max_group, 256) + 31) / 32 * 32);
+        p.tmax = tmax ? tmax : 32;
+        p.err = m_work.p + 1;
+        p.out_offset = 0;
+        for (int j = 0; j < nres; ++j) {
+            if (where == RK_DEVICE) {
+                p.out[j] = static_cast<F *>(out[j]);
+            } else {
+                m_out[j].reserve(n, 1.05);
+                p.out[j] = m_out[j].p;
+            }
+        }
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[4], m_stream));
+        RK_CUDA_CHECK(cudaMemsetAsync(m_work.p, 0, 4 * sizeof(u32), m_stream));
+        RK_CUDA_CHECK(cudaMemsetAsync(m_counters.p, 0, 8 * sizeof(u64), m_stream));
+        const bool partial = (c0 != 0 || c1 != C);
+        if (partial && ordered && where == RK_HOST) {
+            for (int j = 0; j < nres; ++j) {
+                RK_CUDA_CHECK(cudaMemsetAsync(p.out[j], 0, n * sizeof(F), m_stream));
+            }
+        }
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
+        launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream);
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
+        // particle range covered by [c0, c1)
+        size_t pb = 0, pe = n;
+        if (partial) {
+            host_crit_begin();
+            pb = m_h_crit_begin[c0];
+            pe = m_h_crit_begin[c1];
+        }
+        if (where == RK_HOST) {
+            for (int j = 0; j < nres; ++j) {
+                if (ordered) {
+                    RK_CUDA_CHECK(cudaMemcpyAsync(out[j], p.out[j], n * sizeof(F), cudaMemcpyDeviceToHost, m_stream));
+                } else {
+                    RK_CUDA_CHECK(cudaMemcpyAsync(static_cast<F *>(out[j]) + pb, p.out[j] + pb, (pe - pb) * sizeof(F),
+                                                  cudaMemcpyDeviceToHost, m_stream));
+                }
+            }
+        }
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 8, m_work.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[7], m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        const u32 *hw = reinterpret_cast<const u32 *>(m_hpin + 8);
+        if (hw[1]) {
+            throw api_error(RK_ERR_RUNTIME, "Traversal stack overflow in the CUDA kernel");
+        }
+        m_costs_valid = !partial;
+        if (info) {
+            info->mac_tests = m_hpin[0];
+            info->accepted = m_hpin[1];
+            info->p2p_pairs = m_hpin[2];
+            info->self_pairs = m_hpin[3];
+            info->n_groups = c1 - c0;
+            info->kernel_launches = 1;
+            RK_CUDA_CHECK(cudaEventElapsedTime(&info->ms_kernel, m_ev.ev[5], m_ev.ev[6]));
+            RK_CUDA_CHECK(cudaEventElapsedTime(&info->ms_total, m_ev.ev[4], m_ev.ev[7]));
+            // interactions = sum over groups of T*(leaf sources + accepted) + T*(T-1)
+            info->interactions = info->p2p_pairs + 2 * info->self_pairs + m_hpin[4]; // [4] = sum T * accepted
+        }
+    }
+
+    void exact(size_t idx, bool ordered, double G, double eps_d, double out4[4])
+    {
+        use();
+        const F eps = static_cast<F>(eps_d);
+        if (!std::isfinite(eps) || eps < F(0)) {
+            throw api_error(RK_ERR_DOMAIN, "The softening length must be finite and non-negative, but it is "
+                                               + std::to_string(eps) + " instead");
+        }
+        const F eps2 = eps * eps;
+        if (!std::isfinite(eps2) || eps2 < F(0)) {
+            throw api_error(RK_ERR_DOMAIN,
+                            "The square of the softening length must be finite and non-negative, but it is "
+                                + std::to_string(eps2) + " instead");
+        }
+        if (!std::isfinite(static_cast<F>(G))) {
+            throw api_error(RK_ERR_DOMAIN, "The value of the gravitational constant G must be finite, but it is "
+                                               + std::to_string(static_cast<F>(G)) + " instead");
+        }
+        if (idx >= m_b.n) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "Particle index out of range");
+        }
+        if (ordered) {
+            u32 v;
+            RK_CUDA_CHECK(cudaMemcpyAsync(&v, m_b.inv_perm.p + idx, sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+            idx = v;
+        }
+        double *d = reinterpret_cast<double *>(m_counters.p) + 4;
+        launch_exact<F>(m_b.psorted.p, m_b.n, idx, static_cast<F>(G), eps2, d, m_stream);
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 16, d, 4 * sizeof(double), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        std::memcpy(out4, m_hpin + 16, 4 * sizeof(double));
+    }
+
+private:
+    void reserve_particles(size_t n)
+    {
+        m_b.pin.reserve(n, 1.05);
+        m_b.psorted.reserve(n, 1.05);
+        m_b.keys_a.reserve(n, 1.05);
+        m_b.keys_b.reserve(n, 1.05);
+        m_b.idx_a.reserve(n, 1.05);
+        m_b.idx_b.reserve(n, 1.05);
+        m_b.perm.reserve(n, 1.05);
+        m_b.perm_tmp.reserve(n, 1.05);
+        m_b.inv_perm.reserve(n, 1.05);
+    }
+    void reset_flags()
+    {
+        RK_CUDA_CHECK(cudaMemsetAsync(m_b.d_err.p, 0xff, 2 * sizeof(u64), m_stream));
+        RK_CUDA_CHECK(cudaMemsetAsync(m_b.d_misc.p, 0, 8 * sizeof(u32), m_stream));
+    }
+    // Make x, y, z, m available on the device (NULL stays NULL).
+    void upload4(const void *x, const void *y, const void *z, const void *m, size_t n, int where, const F *&dx,
+                 const F *&dy, const F *&dz, const F *&dm)
+    {
+        const void *in[4] = {x, y, z, m};
+        const F *d[4];
+        for (int j = 0; j < 4; ++j) {
+            if (!in[j] || !n) {
+                d[j] = in[j] ? static_cast<const F *>(in[j]) : nullptr;
+                continue;
+            }
+            if (where == RK_DEVICE) {
+                d[j] = static_cast<const F *>(in[j]);
+            } else {
+                m_b.stage[j].reserve(n, 1.05);
+                RK_CUDA_CHECK(cudaMemcpyAsync(m_b.stage[j].p, in[j], n * sizeof(F), cudaMemcpyHostToDevice, m_stream));
+                d[j] = m_b.stage[j].p;
+            }
+        }
+        dx = d[0];
+        dy = d[1];
+        dz = d[2];
+        dm = d[3];
+    }
+
+    // Encode -> sort -> permute -> topology -> properties, shared by build() and update_positions().
+    void rebuild(bool first, rk_build_info *info)
+    {
+        const size_t n = m_b.n;
+        if (info) {
+            std::memset(info, 0, sizeof(*info));
+        }
+        if (!n) {
+            if (m_box_deduced) {
+                m_box = F(0);
+            }
+            if (info) {
+                info->box_size = m_box;
+            }
+            return;
+        }
+        // ---- box size, determine_box_size tree.hpp:1278-1319 ----
+        if (m_box_deduced) {
+            RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_misc.p, sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+            F mx;
+            if (sizeof(F) == 4) {
+                const u32 bits = static_cast<u32>(m_hpin[0]);
+                std::memcpy(&mx, &bits, 4);
+            } else {
+                std::memcpy(&mx, &m_hpin[0], 8);
+            }
+            if (!std::isfinite(mx)) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT, "While trying to automatically determine the domain size, a "
+                                                         "non-finite coordinate with absolute value "
+                                                             + std::to_string(std::abs(mx)) + " was encountered");
+            }
+            F b = mx * F(2);
+            b = std::fma(b, F(1) / F(20), b);
+            if (!std::isfinite(b)) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT,
+                                "The automatic deduction of the domain size produced the non-finite value "
+                                    + std::to_string(b));
+            }
+            m_box = b;
+        }
+        const F inv_box = F(1) / m_box;
+        // ---- Morton encoding ----
+        launch_encode<F>(m_b.pin.p, m_b.keys_a.p, n, inv_box, m_b.d_err.p, m_stream);
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[1], m_stream));
+        // ---- sort (includes one sync for the varying-bits mask) ----
+        u64 *codes;
+        u32 *lperm;
+        const int passes
+            = radix_sort_pairs(m_b.keys_a.p, m_b.keys_b.p, m_b.idx_a.p, m_b.idx_b.p, n, m_sc, m_stream, &codes, &lperm);
+        m_b.codes = codes;
+        m_b.last_perm = lperm;
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[2], m_stream));
+        // ---- permute ----
+        launch_gather<F>(m_b.pin.p, lperm, m_b.psorted.p, n, m_stream);
+        if (first) {
+            launch_perm_first(lperm, m_b.perm.p, m_b.inv_perm.p, n, m_stream);
+        } else {
+            launch_perm_compose(m_b.perm.p, lperm, m_b.perm_tmp.p, m_b.inv_perm.p, n, m_stream);
+            std::swap(m_b.perm.p, m_b.perm_tmp.p);
+            std::swap(m_b.perm.cap, m_b.perm_tmp.cap);
+        }
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[3], m_stream));
+        // ---- topology: count, size, emit ----
+        topology_count<F>(m_b, m_max_leaf_n, m_ncrit, m_stream);
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_err.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(
+            cudaMemcpyAsync(m_hpin + 2, m_b.rowtot.p, (NLEVELS + 1) * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        check_encode_error(m_hpin[0], inv_box);
+        const u32 *rt = reinterpret_cast<const u32 *>(m_hpin + 2);
+        u64 M = 0;
+        for (int l = 0; l < NLEVELS; ++l) {
+            m_b.levels.base[l] = static_cast<u32>(M);
+            M += rt[l];
+        }
+        if (M > 0xfffffff0ull / 8) {
+            throw api_error(RK_ERR_OVERFLOW, "The size of the tree (" + std::to_string(M)
+                                                 + ") is too large, and it results in an overflow condition");
+        }
+        m_b.levels.base[NLEVELS] = static_cast<u32>(M);
+        m_b.levels.base[NLEVELS + 1] = static_cast<u32>(M);
+        const u64 C = rt[NLEVELS];
+        m_b.n_nodes = M;
+        m_b.n_crit = C;
+        m_b.nodeA.reserve(M, 1.1);
+        m_b.nodeB.reserve(M, 1.1);
+        m_b.node_dfs.reserve(M, 1.1);
+        m_b.node_ndesc.reserve(M, 1.1);
+        if (m_mac == RK_MAC_BH_GEOM) {
+            m_b.node_delta.reserve(M, 1.1);
+        }
+        m_b.crit_node.reserve(C, 1.1);
+        m_b.crit_begin.reserve(C + 1, 1.1);
+        topology_emit<F>(m_b, m_stream);
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[4], m_stream));
+        // ---- node properties ----
+        node_properties<F>(m_b, m_mac, m_box, m_stream);
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_err.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 2, m_b.d_misc.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        check_props_error(m_hpin[1]);
+        m_max_group = reinterpret_cast<const u32 *>(m_hpin + 2)[2];
+        m_costs_valid = false;
+        m_h_crit_begin.clear();
+        if (info) {
+            info->box_size = m_box;
+            info->n_nodes = M;
+            info->n_crit = C;
+            info->max_group = m_max_group;
+            info->sort_passes = static_cast<uint32_t>(passes);
+            cudaEventElapsedTime(&info->ms_total, m_ev.ev[0], m_ev.ev[5]);
+            cudaEventElapsedTime(&info->ms_encode, m_ev.ev[0], m_ev.ev[1]);
+            cudaEventElapsedTime(&info->ms_sort, m_ev.ev[1], m_ev.ev[2]);
+            cudaEventElapsedTime(&info->ms_permute, m_ev.ev[2], m_ev.ev[3]);
+            cudaEventElapsedTime(&info->ms_topology, m_ev.ev[3], m_ev.ev[4]);
+            cudaEventElapsedTime(&info->ms_props, m_ev.ev[4], m_ev.ev[5]);
+        }
+    }
+
+    // Messages of disc_single_coord, tree.hpp:398-426.
+    void check_encode_error(u64 key, F inv_box)
+    {
+        if (key == ~0ull) {
+            return;
+        }
+        const u32 cls = static_cast<u32>(key & 0xf), dim = static_cast<u32>((key >> 4) & 0xf);
+        const size_t idx = static_cast<size_t>(key >> 8);
+        vec4<F> v;
+        RK_CUDA_CHECK(cudaMemcpy(&v, m_b.pin.p + idx, sizeof(v), cudaMemcpyDeviceToHost));
+        const F x = dim == 0 ? v.x : (dim == 1 ? v.y : v.z);
+        F tmp = std::fma(x, inv_box, F(1) / F(2));
+        tmp *= F(u64(1) << CBITS);
+        const std::string head = "The discretisation of the input coordinate " + std::to_string(x) + " in a box of size "
+                                 + std::to_string(F(1) / inv_box);
+        if (cls == 1) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "While trying to discretise the input coordinate "
+                                                         + std::to_string(x) + " in a box of size "
+                                                         + std::to_string(F(1) / inv_box) + ", the non-finite value "
+                                                         + std::to_string(tmp) + " was generated");
+        }
+        if (cls == 2) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, head + " produced the floating-point value " + std::to_string(tmp)
+                                                         + ", which is outside the allowed bounds");
+        }
+        throw api_error(RK_ERR_INVALID_ARGUMENT, head + " produced the integral value "
+                                                     + std::to_string(static_cast<u64>(tmp))
+                                                     + ", which is outside the allowed bounds");
+    }
+    // Messages of compute_node_properties, tree.hpp:1195-1235.
+    void check_props_error(u64 key)
+    {
+        if (key == ~0ull) {
+            return;
+        }
+        const u32 cls = static_cast<u32>(key & 0xff);
+        if (cls == 5) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT,
+                            "The computation of the centre of mass of a node produced a non-finite value");
+        }
+        if (cls == 6) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT,
+                            "The computation of the total mass in a node produced the non-finite value inf");
+        }
+        throw api_error(RK_ERR_INVALID_ARGUMENT, "The computation of the distance between the centre of mass "
+                                                 "and the geometric centre of a node produced the non-finite value inf");
+    }
+    void host_crit_begin()
+    {
+        if (m_h_crit_begin.size() == m_b.n_crit + 1) {
+            return;
+        }
+        m_h_crit_begin.resize(m_b.n_crit + 1);
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_h_crit_begin.data(), m_b.crit_begin.p, (m_b.n_crit + 1) * sizeof(u32),
+                                      cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+
+    int m_mac, m_device, m_sm_count = 148;
+    cudaStream_t m_stream = nullptr, m_own_stream = nullptr;
+    timer_events m_ev;
+    build_arrays<F> m_b;
+    sort_scratch m_sc;
+    F m_box = F(0);
+    bool m_box_deduced = false;
+    size_t m_max_leaf_n = 16, m_ncrit = 128, m_max_group = 0;
+    dbuf<F> m_out[4];
+    dbuf<u64> m_group_cost, m_counters;
+    dbuf<u32> m_work;
+    bool m_costs_valid = false;
+    u64 *m_hpin = nullptr; // pinned scratch for small read-backs
+    std::vector<u32> m_h_crit_begin;
+};
+
+} // namespace rk
+
+struct rk_tree {
+    int fp = 32, mac = 0;
+    rk::tree<float> *t32 = nullptr;
+    rk::tree<double> *t64 = nullptr;
+    std::string err;
+    std::mutex mu;
+};
+
+namespace
+{
+thread_local std::string g_create_error;
+
+template <typename Fn>
+int guarded(rk_tree *t, Fn &&fn)
+{
+    if (!t) {
+        return RK_ERR_INVALID_ARGUMENT;
+    }
+    std::lock_guard<std::mutex> lock(t->mu);
+    try {
+        fn();
+        return RK_OK;
+    } catch (const rk::api_error &e) {
+        t->err = e.what();
+        return e.status;
+    } catch (const rk::cuda_error &e) {
+        t->err = e.what();
+        return e.status;
+    } catch (const std::bad_alloc &) {
+        t->err = "bad_alloc";
+        return RK_ERR_BAD_ALLOC;
+    } catch (const std::exception &e) {
+        t->err = e.what();
+        return RK_ERR_RUNTIME;
+    }
+}
+} // namespace
+
+#define RK_WITH(t, expr)                                                                                               \
+    do {                                                                                                               \
+        if ((t)->fp == 32) {                                                                                           \
+            auto &T = *(t)->t32;                                                                                       \
+            expr;                                                                                                      \
+        } else {                                                                                                       \
+            auto &T = *(t)->t64;                                                                                       \
+            expr;                                                                                                      \
+        }                                                                                                              \
+    } while (0)
+
+extern "C" {
+
+unsigned rk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n < 0 ? 0u : static_cast<unsigned>(n);
+}
+
+unsigned rk_min_size(void)
+{
+    return 1000u; // same threshold as the reference, rakau_cuda.cu:26-29
+}
+
+rk_tree *rk_tree_create(int fp_bits, int mac, int device)
+{
+    g_create_error.clear();
+    if ((fp_bits != 32 && fp_bits != 64) || (mac != RK_MAC_BH && mac != RK_MAC_BH_GEOM)) {
+        g_create_error = "rk_tree_create: fp_bits must be 32 or 64 and mac RK_MAC_BH or RK_MAC_BH_GEOM";
+        return nullptr;
+    }
+    if (rk_device_count() == 0) {
+        g_create_error = "rk_tree_create: no CUDA device is available (librakau_b200 has no CPU fallback)";
+        return nullptr;
+    }
+    rk_tree *t = nullptr;
+    try {
+        t = new rk_tree;
+        t->fp = fp_bits;
+        t->mac = mac;
+        if (fp_bits == 32) {
+            t->t32 = new rk::tree<float>(mac, device);
+        } else {
+            t->t64 = new rk::tree<double>(mac, device);
+        }
+        return t;
+    } catch (const std::exception &e) {
+        g_create_error = e.what();
+        delete t;
+        return nullptr;
+    }
+}
+
+void rk_tree_destroy(rk_tree *t)
+{
+    if (t) {
+        delete t->t32;
+        delete t->t64;
+        delete t;
+    }
+}
+
+const char *rk_last_error(const rk_tree *t)
+{
+    return t ? t->err.c_str() : "null tree handle";
+}
+const char *rk_create_error(void)
+{
+    return g_create_error.c_str();
+}
+
+int rk_tree_set_stream(rk_tree *t, void *s)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.set_stream(s)); });
+}
+int rk_tree_synchronize(rk_tree *t)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.synchronize()); });
+}
+
+int rk_tree_build(rk_tree *t, const void *x, const void *y, const void *z, const void *m, size_t n, int where,
+                  double box_size, int deduce_box, size_t max_leaf_n, size_t ncrit, rk_build_info *info)
+{
+    return guarded(
+        t, [&]() { RK_WITH(t, T.build(x, y, z, m, n, where, box_size, deduce_box != 0, max_leaf_n, ncrit, info)); });
+}
+int rk_tree_update_positions(rk_tree *t, const void *x, const void *y, const void *z, int where, rk_build_info *info)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.update_positions(x, y, z, where, info)); });
+}
+int rk_tree_update_masses(rk_tree *t, const void *m, int where)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.update_masses(m, where)); });
+}
+int rk_tree_clear(rk_tree *t)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.clear()); });
+}
+
+size_t rk_tree_nparts(const rk_tree *t)
+{
+    return t->fp == 32 ? t->t32->nparts() : t->t64->nparts();
+}
+size_t rk_tree_nnodes(const rk_tree *t)
+{
+    return t->fp == 32 ? t->t32->nnodes() : t->t64->nnodes();
+}
+size_t rk_tree_ncrit(const rk_tree *t)
+{
+    return t->fp == 32 ? t->t32->ncrit_nodes() : t->t64->ncrit_nodes();
+}
+double rk_tree_box_size(const rk_tree *t)
+{
+    return t->fp == 32 ? t->t32->box_size() : t->t64->box_size();
+}
+int rk_tree_get_parts(rk_tree *t, void *x, void *y, void *z, void *m)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_parts(x, y, z, m)); });
+}
+int rk_tree_get_codes(rk_tree *t, uint64_t *codes)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_codes(codes)); });
+}
+int rk_tree_get_perm(rk_tree *t, int which, uint64_t *out)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_perm(which, out)); });
+}
+int rk_tree_get_nodes(rk_tree *t, void *nodes)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_nodes(nodes)); });
+}
+int rk_tree_get_crit(rk_tree *t, rk_cnode *crit)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_crit(crit)); });
+}
+int rk_tree_get_group_costs(rk_tree *t, uint64_t *costs)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_group_costs(costs)); });
+}
+
+int rk_tree_acc_pot(rk_tree *t, int Q, int ordered, double theta, double G, double eps, const double *split,
+                    size_t nsplit, void *const out[4], int where, rk_eval_info *info)
+{
+    return guarded(t, [&]() {
+        RK_WITH(t, T.acc_pot(Q, ordered != 0, theta, G, eps, split, nsplit, false, 0, 0, out, where, info));
+    });
+}
+int rk_tree_acc_pot_range(rk_tree *t, int Q, int ordered, double theta, double G, double eps, size_t crit_begin,
+                          size_t crit_end, void *const out[4], int where, rk_eval_info *info)
+{
+    return guarded(t, [&]() {
+        RK_WITH(t, T.acc_pot(Q, ordered != 0, theta, G, eps, nullptr, 0, true, crit_begin, crit_end, out, where, info));
+    });
+}
+int rk_tree_exact(rk_tree *t, size_t idx, int ordered, double G, double eps, double out4[4])
+{
+    return guarded(t, [&]() { RK_WITH(t, T.exact(idx, ordered != 0, G, eps, out4)); });
+}
+
+int rk_traverse_external_tree(int, int, int, void *const[4], const uint64_t *, size_t, const void *, size_t,
+                              const void *const[4], const uint64_t *, size_t, double, double, double, int, size_t,
+                              rk_eval_info *, char *errbuf, size_t errbuf_len)
+{
+    if (errbuf && errbuf_len) {
+        std::strncpy(errbuf, "rk_traverse_external_tree: not implemented yet", errbuf_len - 1);
+        errbuf[errbuf_len - 1] = 0;
+    }
+    return RK_ERR_RUNTIME;
+}
+
+} // extern "C"

@@ -1,0 +1,203 @@
+// sort.cu — hand-rolled stable LSD radix sort of (63-bit Morton code, u32 index) pairs for sm_100a.
+//
+// Replaces the reference's indirect tbb::parallel_sort (tree.hpp:1266-1274). The reference sort is
+// unstable; the stable order is one of its legal outcomes and is the canonical one here (SURVEY §7,
+// hard part 2). No CUB/Thrust.
+//
+// Per 8-bit pass: tile_hist (per-tile digit counts, digit-major) -> row_scan (one CTA per digit scans its
+// row over tiles) -> scatter (re-reads the tile, warp-level MATCH.ANY ranking, stable scatter).
+// Passes whose digit is constant over all keys are skipped (found with one OR-reduction over key^key0):
+// on a Plummer sphere the deduced box is ~1e3 core radii, so the top digits are nearly constant.
+// All kernels are HBM-bound: 8 B key read (hist) + 12 B read + 12 B write (scatter) per element per pass.
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace rk
+{
+
+namespace
+{
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_IPT = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT; // 4096 keys per CTA
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int WARP_SPAN = 32 * SORT_IPT; // 512 consecutive keys per warp
+
+// OR over (key ^ key[0]): a digit with no bit set in the result is constant over the whole input.
+__global__ void __launch_bounds__(256) key_or_kernel(const u64 *__restrict__ keys, size_t n, u64 *__restrict__ out)
+{
+    const u64 k0 = keys[0];
+    u64 acc = 0;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        acc |= keys[i] ^ k0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if ((threadIdx.x & 31) == 0 && acc) {
+        atomicOr(out, acc);
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+    tile_hist_kernel(const u64 *__restrict__ keys, size_t n, int shift, u32 ntiles, u32 *__restrict__ tilehist)
+{
+    __shared__ u32 hist[257];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < 257; i += SORT_THREADS) {
+        hist[i] = 0;
+    }
+    __syncthreads();
+    const size_t wbase = size_t(blockIdx.x) * SORT_TILE + size_t(w) * WARP_SPAN;
+#pragma unroll 4
+    for (int j = 0; j < SORT_IPT; ++j) {
+        const size_t i = wbase + size_t(j) * 32 + lane;
+        const bool valid = i < n;
+        const u32 d = valid ? static_cast<u32>((keys[i] >> shift) & 0xffu) : 256u;
+        const u32 peers = __match_any_sync(0xffffffffu, d);
+        if (lane == __ffs(peers) - 1) {
+            atomicAdd(&hist[d], __popc(peers));
+        }
+    }
+    __syncthreads();
+    if (tid < 256) {
+        tilehist[size_t(tid) * ntiles + blockIdx.x] = hist[tid];
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+    scatter_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ idx_in, u64 *__restrict__ keys_out,
+                   u32 *__restrict__ idx_out, size_t n, int shift, u32 ntiles, const u32 *__restrict__ tilehist,
+                   const u32 *__restrict__ totals)
+{
+    __shared__ u32 wcnt[SORT_WARPS][257];
+    __shared__ u32 ws[8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < SORT_WARPS * 257; i += SORT_THREADS) {
+        (&wcnt[0][0])[i] = 0;
+    }
+    // Global base of each digit = exclusive scan of the row totals.
+    u32 dummy;
+    const u32 dbase = block_exscan_256(totals[tid], ws, &dummy); // also syncs after zeroing wcnt
+
+    const size_t wbase = size_t(blockIdx.x) * SORT_TILE + size_t(w) * WARP_SPAN;
+    u64 key[SORT_IPT];
+    unsigned short rank[SORT_IPT];
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < SORT_IPT; ++j) {
+        const size_t i = wbase + size_t(j) * 32 + lane;
+        const bool valid = i < n;
+        key[j] = valid ? keys_in[i] : ~0ull;
+        const u32 d = valid ? static_cast<u32>((key[j] >> shift) & 0xffu) : 256u;
+        const u32 peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        u32 old = 0;
+        if (lane == leader) {
+            old = wcnt[w][d];
+            wcnt[w][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[j] = static_cast<unsigned short>(old + __popc(peers & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+    // Turn the per-warp counts into global write bases: digit base + tiles before + warps before.
+    {
+        u32 run = dbase + tilehist[size_t(tid) * ntiles + blockIdx.x];
+#pragma unroll
+        for (int k = 0; k < SORT_WARPS; ++k) {
+            const u32 c = wcnt[k][tid];
+            wcnt[k][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SORT_IPT; ++j) {
+        const size_t i = wbase + size_t(j) * 32 + lane;
+        if (i < n) {
+            const u32 d = static_cast<u32>((key[j] >> shift) & 0xffu);
+            const u32 pos = wcnt[w][d] + rank[j];
+            keys_out[pos] = key[j];
+            idx_out[pos] = idx_in ? idx_in[i] : static_cast<u32>(i);
+        }
+    }
+}
+
+__global__ void iota_kernel(u32 *p, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        p[i] = static_cast<u32>(i);
+    }
+}
+
+} // namespace
+
+void launch_iota(u32 *p, size_t n, cudaStream_t st)
+{
+    if (n) {
+        iota_kernel<<<div_up(n, 256), 256, 0, st>>>(p, n);
+    }
+}
+
+int radix_sort_pairs(u64 *keys_a, u64 *keys_b, u32 *idx_a, u32 *idx_b, size_t n, sort_scratch &sc, cudaStream_t st,
+                     u64 **keys_out, u32 **idx_out)
+{
+    *keys_out = keys_a;
+    *idx_out = idx_a;
+    if (n == 0) {
+        return 0;
+    }
+    const u32 ntiles = div_up(n, SORT_TILE);
+    sc.ghist.reserve(256 + 8);
+    sc.tilehist.reserve(size_t(256) * ntiles, 1.25);
+    if (!sc.h_ghist) {
+        RK_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&sc.h_ghist), 16 * sizeof(u32)));
+    }
+    u64 *d_or = reinterpret_cast<u64 *>(sc.ghist.p + 256); // 8-byte aligned: cudaMalloc base + 1024 B
+    RK_CUDA_CHECK(cudaMemsetAsync(d_or, 0, sizeof(u64), st));
+    key_or_kernel<<<592, 256, 0, st>>>(keys_a, n, d_or);
+    RK_CUDA_CHECK(cudaMemcpyAsync(sc.h_ghist, d_or, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    RK_CUDA_CHECK(cudaStreamSynchronize(st));
+    u64 varying;
+    static_assert(sizeof(u64) == 2 * sizeof(u32), "");
+    varying = *reinterpret_cast<u64 *>(sc.h_ghist);
+
+    u64 *kin = keys_a, *kout = keys_b;
+    u32 *iin = nullptr, *iout = idx_b; // first pass: implicit iota, write into idx_b
+    u32 *ibufs[2] = {idx_a, idx_b};
+    int passes = 0;
+    for (int shift = 0; shift < 63; shift += 8) {
+        if (((varying >> shift) & 0xffull) == 0) {
+            continue;
+        }
+        tile_hist_kernel<<<ntiles, SORT_THREADS, 0, st>>>(kin, n, shift, ntiles, sc.tilehist.p);
+        row_scan_kernel<<<256, 256, 0, st>>>(sc.tilehist.p, ntiles, sc.ghist.p);
+        scatter_kernel<<<ntiles, SORT_THREADS, 0, st>>>(kin, iin, kout, iout, n, shift, ntiles, sc.tilehist.p,
+                                                        sc.ghist.p);
+        ++passes;
+        u64 *tk = kin;
+        kin = kout;
+        kout = tk;
+        iin = iout;
+        iout = (iin == ibufs[0]) ? ibufs[1] : ibufs[0];
+    }
+    if (passes == 0) {
+        // All keys equal: identity permutation.
+        launch_iota(idx_a, n, st);
+        *keys_out = keys_a;
+        *idx_out = idx_a;
+    } else {
+        *keys_out = kin;
+        *idx_out = iin;
+    }
+    RK_CUDA_CHECK(cudaGetLastError());
+    return passes;
+}
+
+} // namespace rk
