@@ -5,13 +5,17 @@ NVFLAGS   = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidde
 CSRC      = rakau_b200/csrc
 OBJDIR    = build
 LIB       = rakau_b200/lib/librakau_b200.so
-OBJS      = $(OBJDIR)/sort.o $(OBJDIR)/build.o $(OBJDIR)/traverse.o $(OBJDIR)/capi.o
+OBJS      = $(OBJDIR)/sort.o $(OBJDIR)/build.o $(OBJDIR)/traverse.o $(OBJDIR)/capi.o $(OBJDIR)/plummer.o
 
 all: $(LIB) oracle
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/scan.cuh include/rakau_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+$(OBJDIR)/plummer.o: $(CSRC)/plummer.cpp include/rakau_b200.h
+	@mkdir -p $(OBJDIR)
+	g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -pthread -c $< -o $@
 
 $(LIB): $(OBJS)
 	@mkdir -p rakau_b200/lib

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Barnes-Hut hot path (BASELINE.json): one "step" = one acceleration
+evaluation = tree build (Morton encode, sort, octree, node properties) + ncrit-grouped traversal.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+
+N = 1: BASELINE config 1 (3D Plummer, 4M particles, fp32, theta = 0.75, accelerations, max_leaf_n 16,
+ncrit 128 — the parameters behind the reference's published table). N > 1: BASELINE config 5 (128M
+particles, strong scaling): inputs sharded over the ranks, all-gathered with NCCL, identical tree on every
+GPU, critical nodes sharded by cost-weighted Morton ranges, outputs all-gathered.
+
+Prints ONE JSON line (rank 0). `value` = interactions / device time with inputs resident in HBM;
+`e2e` = the same through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region).
+`--impl reference` times the reference's CPU algorithm on the host cores (oracle/_ref when it was built,
+else the scalar oracle port) — the only place besides `cpu_baseline` where oracle/ is executed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Ginteractions/s (accel eval = tree build + traversal, Plummer, theta=0.75, fp32; ms per accel eval in ms_per_step)"
+SLOTS_PER_INTERACTION = 12  # FP32 issue slots per pair (3 FADD + 3 FFMA + 3 FMUL + 3 FFMA), SURVEY §8(d) conv. B
+FLOP_PER_INTERACTION_LIT = 20  # literature convention A
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nparts", type=int, default=0, help="0 = 4M for one GPU, 128M otherwise")
+    ap.add_argument("--theta", type=float, default=0.75)
+    ap.add_argument("--max-leaf-n", type=int, default=16)
+    ap.add_argument("--ncrit", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.path = f"/tmp/rk_clocks_{os.getpid()}.csv"
+        self.p = None
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            # "under load": the upper half of the samples (idle gaps between steps pull the clock down)
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the ONLY users of oracle/ in this file)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, nparts, steps, warmup, target_seconds):
+    """Times the reference's CPU algorithm on the host cores on a bounded sample of the workload.
+
+    Build is run once in full; each step traverses every `stride`-th critical node with all host threads and
+    is extrapolated to the full evaluation by interaction count."""
+    import oracle  # noqa: test infrastructure, allowed here only
+    import rakau_b200 as rk
+    cores = os.cpu_count() or 1
+    m, x, y, z = rk.plummer(nparts)
+    kind = "port"
+    t0 = time.time()
+    tree = oracle.OracleTree(x, y, z, m, max_leaf_n=args.max_leaf_n, ncrit=args.ncrit)
+    t_build = time.time() - t0
+    ncrit_nodes = len(tree.crit()[0])
+    # probe to size the sample
+    probe_stride = max(1, ncrit_nodes // 2000)
+    t0 = time.time()
+    c = tree.acc_pot_sample(0, args.theta, probe_stride, 0, nthreads=cores)
+    t_probe = max(time.time() - t0, 1e-4)
+    est_full = t_probe * probe_stride
+    nsteps = max(1, steps + warmup)
+    stride = max(1, int(np.ceil(est_full * nsteps / max(target_seconds, 1.0))))
+    times, inter = [], []
+    for s in range(nsteps):
+        t0 = time.time()
+        c = tree.acc_pot_sample(0, args.theta, stride, s % stride, nthreads=cores)
+        dt = time.time() - t0
+        if s >= warmup:
+            times.append(dt)
+            inter.append(c["interactions"])
+    rate = sum(inter) / sum(times)  # interactions / s of the traversal
+    # full-evaluation estimate: total interactions from the strided samples
+    i_total = float(np.mean(inter)) * stride
+    t_full = t_build + i_total / rate
+    value = i_total / t_full / 1e9
+    sample = (f"oracle scalar port: full build once ({t_build:.2f} s, 1 thread) + traversal of every {stride}-th "
+              f"critical node per step ({len(times)} timed steps, {cores} threads, {sum(times):.1f} s CPU wall); "
+              f"extrapolated by interaction count")
+    return dict(value=value, ms_per_step=t_full * 1e3, cores=cores, kind=kind, sample=sample,
+                traversal_ginter_s=rate / 1e9, build_s=t_build, interactions=i_total)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nparts = args.nparts or 4_000_000  # the reference arm always runs the CPU-runnable config
+    r = cpu_reference_run(args, nparts, args.steps, args.warmup, 90.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Ginteractions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"plummer_{nparts}_fp32_theta{args.theta}_accs", "max_leaf_n": args.max_leaf_n,
+                   "ncrit": args.ncrit, "nparts": nparts},
+        "cpu_baseline": {"value": r["value"], "unit": "Ginteractions/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "Ginteractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def split_by_cost(costs_cum, total, world):
+    """Boundaries (critical-node indices) cutting the cumulative cost into `world` nearly equal parts."""
+    import torch
+    targets = torch.arange(1, world, device=costs_cum.device, dtype=costs_cum.dtype) * (total // world)
+    cuts = torch.searchsorted(costs_cum, targets).tolist()
+    return [0] + [int(c) + 1 for c in cuts] + [int(costs_cum.numel())]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import rakau_b200 as rk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nparts = args.nparts or (4_000_000 if world == 1 else 128_000_000)
+    chunk = 1 << 20
+    per = (nparts + world - 1) // world
+    per = (per + chunk - 1) // chunk * chunk if world > 1 else nparts
+    first = min(rank * per, nparts)
+    count = max(0, min(nparts, first + per) - first)
+
+    # ---- synthetic inputs: pinned host shards (benchmark/common.hpp Plummer sphere) ----
+    hx, hy, hz, hm = (torch.empty(count, dtype=torch.float32).pin_memory() for _ in range(4))
+    rk.plummer(nparts, first, count, fp=32, chunk=(chunk if world > 1 else 0),
+               out=[hm.numpy(), hx.numpy(), hy.numpy(), hz.numpy()])
+    stream = torch.cuda.current_stream()
+    tree = rk.Octree(fp=32, mac="bh", device=local)
+    tree.set_stream(stream.cuda_stream)
+
+    # resident copies of the shard (inputs in HBM when the timed region starts)
+    dsh = [t.to(dev, non_blocking=True) for t in (hx, hy, hz, hm)]
+    counts = [max(0, min(nparts, min(r * per, nparts) + per) - min(r * per, nparts)) for r in range(world)]
+    full = [torch.empty(nparts, dtype=torch.float32, device=dev) for _ in range(4)] if world > 1 else dsh
+    out_dev = [torch.zeros(nparts, dtype=torch.float32, device=dev) for _ in range(3)]
+    hout = [torch.empty(nparts, dtype=torch.float32).pin_memory() for _ in range(3)]
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
+    state = {"cuts": None, "crit_begin": None, "info": None, "bi": None}
+
+    def gather_inputs(src):
+        if world == 1:
+            return src
+        for j in range(4):
+            if len(set(counts)) == 1:
+                dist.all_gather_into_tensor(full[j], src[j])
+            else:
+                offs = np.cumsum([0] + counts)
+                dist.all_gather([full[j][offs[r]:offs[r + 1]] for r in range(world)], src[j])
+        return full
+
+    def my_range():
+        C = tree.ncrit_nodes
+        if world == 1:
+            return 0, C
+        if state["cuts"] is None:
+            # first evaluation: equal particle counts (tree.hpp:3147-3178 projects shares onto particle indices)
+            cr = tree.crit()[:, 1].astype(np.int64)
+            state["crit_begin"] = np.concatenate([cr, [nparts]])
+            tg = np.arange(1, world, dtype=np.int64) * (nparts // world)
+            state["cuts"] = [0] + np.searchsorted(cr, tg).tolist() + [C]
+        return state["cuts"][rank], state["cuts"][rank + 1]
+
+    def step(e2e):
+        if e2e:
+            src = [t.to(dev, non_blocking=True) for t in (hx, hy, hz, hm)]
+        else:
+            src = dsh
+        f = gather_inputs(src)
+        state["bi"] = tree.build(f[0], f[1], f[2], f[3], max_leaf_n=args.max_leaf_n, ncrit=args.ncrit,
+                                 where=rk.RK_DEVICE, n=nparts)
+        c0, c1 = my_range()
+        tree.acc_pot(0, args.theta, out=out_dev, where=rk.RK_DEVICE, crit_range=(c0, c1) if world > 1 else None)
+        state["info"] = tree.eval_info.asdict()
+        if world > 1:
+            # output exchange: every rank owns the Morton-order slice of the critical nodes it evaluated and
+            # broadcasts it in place, so that all ranks end with the full result (as a leapfrog step needs)
+            cb = state["crit_begin"]
+            cuts = state["cuts"]
+            for r in range(world):
+                pb, pe = int(cb[cuts[r]]), int(cb[cuts[r + 1]])
+                if pe > pb:
+                    for j in range(3):
+                        dist.broadcast(out_dev[j][pb:pe], src=r)
+        if e2e:
+            for j in range(3):
+                hout[j].copy_(out_dev[j], non_blocking=True)
+            stream.synchronize()
+
+    def refresh_costs():
+        if world == 1:
+            return
+        C = tree.ncrit_nodes
+        costs = torch.from_numpy(tree.group_costs().astype(np.int64)).to(dev)
+        dist.all_reduce(costs)
+        cum = torch.cumsum(costs, 0)
+        state["cuts"] = split_by_cost(cum, int(cum[-1].item()), world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        infos = []
+        barrier()
+        for a, b in evs:
+            flush.zero_()  # L2 flush between timed iterations (outside the timed region)
+            a.record()
+            step(e2e)
+            b.record()
+            infos.append((state["info"], state["bi"].asdict()))
+        barrier()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()), ms, infos
+
+    # ---- warm-up (also establishes the cost-weighted split for N > 1) ----
+    for w in range(max(args.warmup, 3)):
+        step(False)
+        if w == 0:
+            refresh_costs()
+    step(True)
+    fp32_peak = rk.measure_fp32_peak(local)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = rk.kernel_launch_count()
+    tot_ms, ms, infos = timed(args.steps, False)
+    launches = rk.kernel_launch_count() - l0
+    clk = clocks.stop()
+    e2e_tot_ms, e2e_ms, _ = timed(args.steps, True)
+
+    # whole-job interactions per step = sum over ranks
+    inter = torch.tensor([infos[-1][0]["interactions"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(inter)
+    inter = float(inter.item())
+    ms_per_step = tot_ms / args.steps
+    value = inter / (ms_per_step * 1e-3) / 1e9
+    e2e_value = inter / (e2e_tot_ms / args.steps * 1e-3) / 1e9
+    k_ms = float(np.mean([i[0]["ms_kernel"] for i in infos]))
+    b_ms = float(np.mean([i[1]["ms_total"] for i in infos]))
+    my_inter = infos[-1][0]["interactions"]
+    achieved = SLOTS_PER_INTERACTION * 2 * my_inter / (k_ms * 1e-3) / 1e12  # FMA-equivalent TFLOP/s
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traverse_kernel_latest.json")))
+        traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    bi = infos[-1][1]
+    # algorithmic build bytes (fp32, u64 codes), SURVEY §8(d): pack 16+16, encode 16+8, sort passes x (8 + 12 + 12),
+    # gather 4+16+16, perms 4+4+4, topology ~12, plus 64 B per node
+    build_bytes = nparts * (32 + 24 + bi["sort_passes"] * 32 + 36 + 12 + 12) + bi["n_nodes"] * 64
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": "Ginteractions/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"plummer_{nparts}_fp32_theta{args.theta}_accs", "nparts": nparts,
+                   "max_leaf_n": args.max_leaf_n, "ncrit": args.ncrit, "mac": "bh", "G": 1.0, "eps": 0.0,
+                   "parallelism": f"morton_range_shard{world}" if world > 1 else "single_gpu",
+                   "l2": "256 MiB buffer written between timed iterations", "interactions_per_step": inter,
+                   "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"]},
+        "ms_build": b_ms, "ms_traverse_kernel": k_ms,
+        "build_phases_ms": {k: bi[k] for k in ("ms_encode", "ms_sort", "ms_permute", "ms_topology", "ms_props")},
+        "roofline": {"bound": "fp32", "kernel": "traverse_kernel<float,0,0>", "achieved": achieved,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
+                     "convention": "12 FP32 issue slots per interaction counted as FMA (2 flop); peak = FFMA "
+                                   "microbenchmark measured in this run",
+                     "gflops_literature_20flop": FLOP_PER_INTERACTION_LIT * my_inter / (k_ms * 1e-3) / 1e9},
+        "roofline_build": {"bound": "hbm", "achieved": build_bytes / (b_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": build_bytes / (b_ms * 1e-3) / 1e9 / hbm_peak,
+                           "peak_source": "measured" if peaks else "fallback"},
+        "e2e": {"value": e2e_value, "unit": "Ginteractions/s", "ms_per_step": e2e_tot_ms / args.steps,
+                "h2d_bytes_per_step": 16 * count, "d2h_bytes_per_step": 12 * nparts},
+        "gpu_launches": int(launches), "clocks": clk,
+        "vs_published_ms": {"note": "reference README traversal-only times, other hardware", "v100_ms": 95,
+                            "xeon6148x2_ms": 82, "ours_traverse_ms": k_ms},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(args, nparts, 3, 1, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "Ginteractions/s", "cores": r["cores"],
+                                    "kind": r["kind"], "sample": r["sample"]}
+        except Exception as e:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

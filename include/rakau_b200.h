@@ -145,6 +145,8 @@ RK_API int rk_tree_acc_pot_range(rk_tree *t, int Q, int ordered, double theta, d
                                  size_t crit_end, void *const out[4], int where, rk_eval_info *info);
 /* Per-critical-node interaction counts of the last full evaluation (cost weights for sharding). */
 RK_API int rk_tree_get_group_costs(rk_tree *t, uint64_t *costs);
+/* Device pointer to the same per-critical-node costs (uint64_t[ncrit]); NULL before the first evaluation. */
+RK_API const void *rk_tree_group_costs_device(rk_tree *t);
 /* exact_acc_pot_impl, tree.hpp:3531-3569: direct sum for one particle. idx in Morton order (ordered=0) or
  * original order (ordered=1). out4 = ax, ay, az, pot. */
 RK_API int rk_tree_exact(rk_tree *t, size_t idx, int ordered, double G, double eps, double out4[4]);
@@ -160,6 +162,20 @@ RK_API int rk_traverse_external_tree(int fp_bits, int mac, int Q, void *const ou
                                      const uint64_t *codes, size_t nparts, double mac_value, double G, double eps2,
                                      int offset_output, size_t ncrit, rk_eval_info *info, char *errbuf,
                                      size_t errbuf_len);
+
+/* ---- synthetic inputs of the reference's benchmarks (host only) ------------------------------------------ */
+/* Plummer sphere of benchmark/common.hpp:39-126. mode 0: sequential branch (first = 0, count = n_total);
+ * mode 1: chunked deterministic form of the parallel branch (chunk seeded with its first index); `first` must be
+ * a multiple of `chunk`, so ranks can generate disjoint shards [first, first + count) of one global stream. */
+RK_API int rk_plummer(int fp_bits, size_t n_total, size_t first, size_t count, double a, double size, int mode,
+                      size_t chunk, int nthreads, void *m, void *x, void *y, void *z);
+
+/* ---- measurement helpers (bench.py) ------------------------------------------------------------------- */
+/* Kernels launched by this library since it was loaded. */
+RK_API unsigned long long rk_kernel_launch_count(void);
+/* FFMA microbenchmark on `device`: measured FP32-pipe peak in TFLOP/s (2 flop per FFMA), the denominator of the
+ * traversal roofline (do not assume the nominal clock). */
+RK_API int rk_measure_fp32_peak(int device, double *tflops, double *ms);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,8 @@ def lib():
         L.orc_get_crit.argtypes = [vp, vp, vp]
         L.orc_acc_pot.restype = i32
         L.orc_acc_pot.argtypes = [vp, i32, dbl, dbl, dbl, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_acc_pot_sample.restype = i32
+        L.orc_acc_pot_sample.argtypes = [vp, i32, dbl, dbl, dbl, vp, vp, vp, vp, vp, i32, sz, sz]
         L.orc_exact.restype = i32
         L.orc_exact.argtypes = [vp, sz, dbl, dbl, vp]
         L.orc_update_positions.restype = i32
@@ -162,6 +164,17 @@ class OracleTree:
         names = ("mac_tests", "accepted", "p2p_pairs", "self_pairs", "interactions", "leaves_opened")
         c = {k: int(v) for k, v in zip(names, cnt)}
         return (out, c, pg) if per_group else (out, c)
+
+    def acc_pot_sample(self, Q, theta, stride, offset=0, G=1.0, eps=0.0, nthreads=1):
+        """Evaluate every stride-th critical node only (CPU-baseline timing). Returns the counters."""
+        nres = {0: 3, 1: 1, 2: 4}[Q]
+        out = [np.zeros(self.nparts, dtype=self.F) for _ in range(nres)]
+        ptrs = [_p(a) for a in out] + [None] * (4 - nres)
+        cnt = np.zeros(6, dtype=np.uint64)
+        self._check(self.L.orc_acc_pot_sample(self.h, Q, float(theta), float(G), float(eps), *ptrs, _p(cnt), nthreads,
+                                              stride, offset))
+        names = ("mac_tests", "accepted", "p2p_pairs", "self_pairs", "interactions", "leaves_opened")
+        return {k: int(v) for k, v in zip(names, cnt)}
 
     def exact(self, idx, G=1.0, eps=0.0):
         out = np.zeros(4, dtype=np.float64)

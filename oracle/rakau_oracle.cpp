@@ -563,7 +563,8 @@ struct tree_t {
 
     // ---- acc_pot_dispatch (tree.hpp:3293-3334) + acc_pot_impl/cpu_run (tree.hpp:2853-3022) ----
     template <unsigned Q>
-    void acc_pot(F theta, F G, F eps, F *const out[4], counters_t &total, u64 *per_group, int nthreads) const
+    void acc_pot(F theta, F G, F eps, F *const out[4], counters_t &total, u64 *per_group, int nthreads,
+                 std::size_t stride = 1, std::size_t offset = 0) const
     {
         if (!std::isfinite(theta) || theta <= F(0)) {
             throw oracle_error(2,
@@ -578,7 +579,8 @@ struct tree_t {
         const F eps2 = compute_eps2(eps);
         check_G(G);
         constexpr int NR = (Q == 0u) ? 3 : (Q == 1u ? 1 : 4);
-        const std::size_t C = crit.size();
+        // Groups offset, offset+stride, ... (stride > 1: bounded sample for CPU-baseline timing).
+        const std::size_t C = crit.size() > offset ? (crit.size() - offset + stride - 1) / stride : 0;
         std::atomic<std::size_t> next{0};
         const int nt = std::max(1, nthreads);
         std::vector<counters_t> tcnt(nt);
@@ -590,7 +592,8 @@ struct tree_t {
                 if (c0 >= C) {
                     break;
                 }
-                for (std::size_t ci = c0; ci < std::min(C, c0 + 16); ++ci) {
+                for (std::size_t cs = c0; cs < std::min(C, c0 + 16); ++cs) {
+                    const std::size_t ci = offset + cs * stride;
                     const u64 tb = crit[ci].begin, ts = crit[ci].end - tb;
                     const F *tp[4];
                     F *res[4] = {nullptr, nullptr, nullptr, nullptr}, *tmp[5];
@@ -972,8 +975,8 @@ ORC_API void orc_get_crit(void *p, u64 *out, u64 *node_idx)
 
 // out0..3: Morton-order outputs. Q=0: ax,ay,az ; Q=1: pot in out0 ; Q=2: ax,ay,az,pot.
 // counters[6]: mac_tests, accepted, p2p_pairs, self_pairs, interactions, leaves_opened.
-ORC_API int orc_acc_pot(void *p, int Q, double theta, double G, double eps, void *o0, void *o1, void *o2, void *o3,
-                        u64 *counters, u64 *per_group, int nthreads)
+static int orc_acc_pot_impl(void *p, int Q, double theta, double G, double eps, void *o0, void *o1, void *o2, void *o3,
+                            u64 *counters, u64 *per_group, int nthreads, std::size_t stride, std::size_t offset)
 {
     auto *h = static_cast<handle_t *>(p);
     return guarded(h, [&]() {
@@ -982,11 +985,11 @@ ORC_API int orc_acc_pot(void *p, int Q, double theta, double G, double eps, void
             using F = decltype(fzero);
             F *out[4] = {static_cast<F *>(o0), static_cast<F *>(o1), static_cast<F *>(o2), static_cast<F *>(o3)};
             if (Q == 0) {
-                t.template acc_pot<0>(F(theta), F(G), F(eps), out, c, per_group, nthreads);
+                t.template acc_pot<0>(F(theta), F(G), F(eps), out, c, per_group, nthreads, stride, offset);
             } else if (Q == 1) {
-                t.template acc_pot<1>(F(theta), F(G), F(eps), out, c, per_group, nthreads);
+                t.template acc_pot<1>(F(theta), F(G), F(eps), out, c, per_group, nthreads, stride, offset);
             } else {
-                t.template acc_pot<2>(F(theta), F(G), F(eps), out, c, per_group, nthreads);
+                t.template acc_pot<2>(F(theta), F(G), F(eps), out, c, per_group, nthreads, stride, offset);
             }
         };
         DISPATCH(h, run(t, 0.f), run(t, 0.));
@@ -999,6 +1002,19 @@ ORC_API int orc_acc_pot(void *p, int Q, double theta, double G, double eps, void
             counters[5] = c.leaves_opened;
         }
     });
+}
+
+ORC_API int orc_acc_pot(void *p, int Q, double theta, double G, double eps, void *o0, void *o1, void *o2, void *o3,
+                        u64 *counters, u64 *per_group, int nthreads)
+{
+    return orc_acc_pot_impl(p, Q, theta, G, eps, o0, o1, o2, o3, counters, per_group, nthreads, 1, 0);
+}
+// Bounded sample: only critical nodes offset, offset+stride, ... are evaluated (outputs of the others untouched).
+ORC_API int orc_acc_pot_sample(void *p, int Q, double theta, double G, double eps, void *o0, void *o1, void *o2,
+                               void *o3, u64 *counters, int nthreads, std::size_t stride, std::size_t offset)
+{
+    return orc_acc_pot_impl(p, Q, theta, G, eps, o0, o1, o2, o3, counters, nullptr, nthreads, stride ? stride : 1,
+                            offset);
 }
 
 // Direct sum for the particle at Morton index idx; out4 = ax, ay, az, pot (as double).

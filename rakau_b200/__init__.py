@@ -32,7 +32,8 @@ SYMBOLS = [
     "rk_tree_update_masses", "rk_tree_clear", "rk_tree_nparts", "rk_tree_nnodes", "rk_tree_ncrit",
     "rk_tree_box_size", "rk_tree_get_parts", "rk_tree_get_codes", "rk_tree_get_perm", "rk_tree_get_nodes",
     "rk_tree_get_crit", "rk_tree_acc_pot", "rk_tree_acc_pot_range", "rk_tree_get_group_costs", "rk_tree_exact",
-    "rk_traverse_external_tree",
+    "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak",
+    "rk_plummer",
 ]
 
 
@@ -104,6 +105,11 @@ def lib():
     L.rk_tree_exact.argtypes = [vp, sz, i32, dbl, dbl, vp]
     L.rk_traverse_external_tree.argtypes = [i32, i32, i32, C.POINTER(vp), vp, sz, vp, sz, C.POINTER(vp), vp, sz,
                                             dbl, dbl, dbl, i32, sz, C.POINTER(EvalInfo), C.c_char_p, sz]
+    L.rk_tree_group_costs_device.restype = vp
+    L.rk_tree_group_costs_device.argtypes = [vp]
+    L.rk_kernel_launch_count.restype = C.c_ulonglong
+    L.rk_measure_fp32_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
+    L.rk_plummer.argtypes = [i32, sz, sz, sz, dbl, dbl, i32, sz, i32, vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -221,6 +227,9 @@ class Octree:
         self._check(self.L.rk_tree_get_crit(self.h, _ptr(out)))
         return out
 
+    def group_costs_device_ptr(self):
+        return self.L.rk_tree_group_costs_device(self.h)
+
     def group_costs(self):
         out = np.empty(self.ncrit_nodes, dtype=np.uint64)
         self._check(self.L.rk_tree_get_group_costs(self.h, _ptr(out)))
@@ -252,3 +261,31 @@ class Octree:
 
 def device_count():
     return lib().rk_device_count()
+
+
+def kernel_launch_count():
+    return lib().rk_kernel_launch_count()
+
+
+def measure_fp32_peak(device=0):
+    """Measured FP32-pipe peak (TFLOP/s, FFMA = 2 flop) on `device`."""
+    tf, ms = C.c_double(), C.c_double()
+    rc = lib().rk_measure_fp32_peak(device, C.byref(tf), C.byref(ms))
+    if rc:
+        raise RuntimeError("rk_measure_fp32_peak failed")
+    return tf.value
+
+
+def plummer(n_total, first=0, count=None, a=1.0, size=0.0, fp=32, chunk=0, nthreads=None, out=None):
+    """Plummer sphere of the reference's benchmarks (benchmark/common.hpp:39-126). chunk == 0: the sequential
+    branch; chunk > 0: deterministic chunked form, shard [first, first+count). Returns m, x, y, z (numpy, or
+    the given `out` arrays/tensors)."""
+    count = n_total if count is None else count
+    if out is None:
+        out = [np.empty(count, dtype=FDT[fp]) for _ in range(4)]
+    nthreads = nthreads or os.cpu_count() or 1
+    rc = lib().rk_plummer(fp, n_total, first, count, a, size, 1 if chunk else 0, chunk, nthreads,
+                          *[_ptr(o) for o in out])
+    if rc:
+        raise ValueError("rk_plummer: invalid arguments")
+    return out

@@ -727,19 +727,19 @@ void window_levels(i8 *a, i8 *bbuf, i8 *lvl, size_t n, size_t w, cudaStream_t st
 {
     const unsigned g = div_up(n, 256);
     if (w >= n) {
-        fill_i8_kernel<<<g, 256, 0, st>>>(lvl, n, i8(0));
+        fill_i8_kernel<<<g, 256, 0, st>>>(lvl, n, i8(0)); count_launch();
         return;
     }
     size_t k = 1;
     i8 *in = a, *out = bbuf;
     while (k * 2 <= w + 1) {
-        window_double_kernel<<<g, 256, 0, st>>>(in, out, n, k);
+        window_double_kernel<<<g, 256, 0, st>>>(in, out, n, k); count_launch();
         i8 *t = in;
         in = out;
         out = t;
         k *= 2;
     }
-    window_final_kernel<<<g, 256, 0, st>>>(in, lvl, n, w + 1 - k);
+    window_final_kernel<<<g, 256, 0, st>>>(in, lvl, n, w + 1 - k); count_launch();
 }
 
 } // namespace
@@ -754,7 +754,7 @@ void launch_pack_absmax(const F *x, const F *y, const F *z, const F *m, vec4<F> 
                         cudaStream_t st)
 {
     if (n) {
-        pack_absmax_kernel<F><<<STREAM_GRID, 256, 0, st>>>(x, y, z, m, out, n, absmax_bits);
+        pack_absmax_kernel<F><<<STREAM_GRID, 256, 0, st>>>(x, y, z, m, out, n, absmax_bits); count_launch();
     }
 }
 template <typename F>
@@ -762,41 +762,41 @@ void launch_set_coords(vec4<F> *p, const F *x, const F *y, const F *z, const F *
                        cudaStream_t st)
 {
     if (n) {
-        set_coords_kernel<F><<<STREAM_GRID, 256, 0, st>>>(p, x, y, z, m, n, absmax_bits);
+        set_coords_kernel<F><<<STREAM_GRID, 256, 0, st>>>(p, x, y, z, m, n, absmax_bits); count_launch();
     }
 }
 template <typename F>
 void launch_unpack(const vec4<F> *in, F *x, F *y, F *z, F *m, size_t n, cudaStream_t st)
 {
     if (n) {
-        unpack_kernel<F><<<div_up(n, 256), 256, 0, st>>>(in, x, y, z, m, n);
+        unpack_kernel<F><<<div_up(n, 256), 256, 0, st>>>(in, x, y, z, m, n); count_launch();
     }
 }
 template <typename F>
 void launch_encode(const vec4<F> *p, u64 *codes, size_t n, F inv_box, dev_error *err, cudaStream_t st)
 {
     if (n) {
-        encode_kernel<F><<<div_up(n, 256), 256, 0, st>>>(p, codes, n, inv_box, reinterpret_cast<u64 *>(err));
+        encode_kernel<F><<<div_up(n, 256), 256, 0, st>>>(p, codes, n, inv_box, reinterpret_cast<u64 *>(err)); count_launch();
     }
 }
 template <typename F>
 void launch_gather(const vec4<F> *pin, const u32 *idx, vec4<F> *pout, size_t n, cudaStream_t st)
 {
     if (n) {
-        gather_kernel<F><<<div_up(n, 256), 256, 0, st>>>(pin, idx, pout, n);
+        gather_kernel<F><<<div_up(n, 256), 256, 0, st>>>(pin, idx, pout, n); count_launch();
     }
 }
 void launch_perm_first(const u32 *last_perm, u32 *perm, u32 *inv_perm, size_t n, cudaStream_t st)
 {
     if (n) {
-        perm_first_kernel<<<div_up(n, 256), 256, 0, st>>>(last_perm, perm, inv_perm, n);
+        perm_first_kernel<<<div_up(n, 256), 256, 0, st>>>(last_perm, perm, inv_perm, n); count_launch();
     }
 }
 void launch_perm_compose(const u32 *old_perm, const u32 *last_perm, u32 *new_perm, u32 *inv_perm, size_t n,
                          cudaStream_t st)
 {
     if (n) {
-        perm_compose_kernel<<<div_up(n, 256), 256, 0, st>>>(old_perm, last_perm, new_perm, inv_perm, n);
+        perm_compose_kernel<<<div_up(n, 256), 256, 0, st>>>(old_perm, last_perm, new_perm, inv_perm, n); count_launch();
     }
 }
 
@@ -815,15 +815,15 @@ void topology_count(build_arrays<F> &b, size_t max_leaf_n, size_t ncrit, cudaStr
     b.rowtot.reserve(NLEVELS + 1);
     const size_t w1 = max_leaf_n, w2 = ncrit > max_leaf_n ? ncrit : max_leaf_n;
     i8 *p1 = b.win_a.p, *p2 = (w2 != w1) ? b.win_a.p + n : nullptr;
-    delta_window_kernel<<<div_up(n, 256), 256, 0, st>>>(b.codes, n, w1, w2, b.delta.p, p1, p2);
+    delta_window_kernel<<<div_up(n, 256), 256, 0, st>>>(b.codes, n, w1, w2, b.delta.p, p1, p2); count_launch();
     window_levels(p1, b.win_b.p, b.lvl_leaf.p, n, w1, st);
     if (p2) {
         window_levels(p2, b.win_b.p, b.lvl_crit.p, n, w2, st);
     } else {
         RK_CUDA_CHECK(cudaMemcpyAsync(b.lvl_crit.p, b.lvl_leaf.p, n, cudaMemcpyDeviceToDevice, st));
     }
-    topo_count_kernel<<<ntiles, TOPO_TILE, 0, st>>>(b.delta.p, b.lvl_leaf.p, b.lvl_crit.p, n, ntiles, b.tilecnt.p);
-    row_scan_kernel<<<NLEVELS + 1, 256, 0, st>>>(b.tilecnt.p, ntiles, b.rowtot.p);
+    topo_count_kernel<<<ntiles, TOPO_TILE, 0, st>>>(b.delta.p, b.lvl_leaf.p, b.lvl_crit.p, n, ntiles, b.tilecnt.p); count_launch();
+    row_scan_kernel<<<NLEVELS + 1, 256, 0, st>>>(b.tilecnt.p, ntiles, b.rowtot.p); count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -835,12 +835,12 @@ void topology_emit(build_arrays<F> &b, cudaStream_t st)
     const u32 M = static_cast<u32>(b.n_nodes), C = static_cast<u32>(b.n_crit);
     topo_emit_kernel<<<ntiles, TOPO_TILE, 0, st>>>(b.delta.p, b.lvl_leaf.p, b.lvl_crit.p, n, ntiles, b.tilecnt.p,
                                                    b.levels, b.nodeB.p, b.node_dfs.p, b.dfsbase.p, b.crit_node.p,
-                                                   b.crit_begin.p, M, C);
+                                                   b.crit_begin.p, M, C); count_launch();
     topo_finalize_kernel<<<div_up(M, 256), 256, 0, st>>>(b.codes, n, b.nodeB.p, b.node_dfs.p, b.dfsbase.p,
-                                                         b.node_ndesc.p, b.levels, M);
-    topo_children_kernel<<<div_up(M, 256), 256, 0, st>>>(b.nodeB.p, b.levels, M);
+                                                         b.node_ndesc.p, b.levels, M); count_launch();
+    topo_children_kernel<<<div_up(M, 256), 256, 0, st>>>(b.nodeB.p, b.levels, M); count_launch();
     RK_CUDA_CHECK(cudaMemsetAsync(b.d_misc.p + 2, 0, sizeof(u32), st));
-    max_group_kernel<<<div_up(C, 256), 256, 0, st>>>(b.crit_begin.p, C, b.d_misc.p + 2);
+    max_group_kernel<<<div_up(C, 256), 256, 0, st>>>(b.crit_begin.p, C, b.d_misc.p + 2); count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -854,10 +854,10 @@ void node_properties(build_arrays<F> &b, int mac, F box_size, cudaStream_t st)
     }
     const u32 nchunks = div_up(n, PROPS_CHUNK);
     b.chunksum.reserve(size_t(nchunks) * 4, 1.05);
-    chunk_sums_kernel<F><<<div_up(size_t(nchunks) * 32, 256), 256, 0, st>>>(b.psorted.p, n, nchunks, b.chunksum.p);
+    chunk_sums_kernel<F><<<div_up(size_t(nchunks) * 32, 256), 256, 0, st>>>(b.psorted.p, n, nchunks, b.chunksum.p); count_launch();
     node_props_kernel<F><<<div_up(size_t(M) * 32, 256), 256, 0, st>>>(
         b.psorted.p, b.codes, b.chunksum.p, b.nodeB.p, b.nodeA.p, b.node_delta.p, M, mac, make_level_dims<F>(box_size),
-        reinterpret_cast<u64 *>(b.d_err.p) + 1);
+        reinterpret_cast<u64 *>(b.d_err.p) + 1); count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -869,7 +869,7 @@ void launch_export_nodes(const build_arrays<F> &b, int mac, F box_size, void *d_
         export_nodes_kernel<F><<<div_up(M, 256), 256, 0, st>>>(b.codes, b.nodeB.p, b.nodeA.p, b.node_delta.p,
                                                                b.node_dfs.p, b.node_ndesc.p, M, mac,
                                                                make_level_dims<F>(box_size),
-                                                               static_cast<host_node<F> *>(d_out));
+                                                               static_cast<host_node<F> *>(d_out)); count_launch();
     }
 }
 
@@ -878,7 +878,7 @@ void launch_export_crit(const u64 *codes, const uint4 *nodeB, const u32 *crit_no
 {
     if (n_crit) {
         export_crit_kernel<<<div_up(n_crit, 256), 256, 0, st>>>(codes, nodeB, crit_node, crit_begin,
-                                                                static_cast<u32>(n_crit), d_out);
+                                                                static_cast<u32>(n_crit), d_out); count_launch();
     }
 }
 

@@ -19,6 +19,8 @@
 namespace rk
 {
 
+unsigned long long g_kernel_launches = 0;
+
 struct api_error : std::runtime_error {
     int status;
     api_error(int st, const std::string &s) : std::runtime_error(s), status(st) {}
@@ -267,15 +269,18 @@ public:
         RK_CUDA_CHECK(cudaMemcpyAsync(crit, tmp.p, 3 * C * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
     }
+    const void *group_costs_device() const { return m_costs_valid ? m_group_cost.p : nullptr; }
     void get_group_costs(uint64_t *costs)
     {
         use();
         if (!m_costs_valid) {
             throw api_error(RK_ERR_INVALID_ARGUMENT, "No evaluation has been run on this tree yet");
         }
-        RK_CUDA_CHECK(
-            cudaMemcpyAsync(costs, m_group_cost.p, m_b.n_crit * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
-        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        if (m_b.n_crit) {
+            RK_CUDA_CHECK(
+                cudaMemcpyAsync(costs, m_group_cost.p, m_b.n_crit * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        }
     }
 
     // ---- acc_pot_dispatch (tree.hpp:3293-3334) + acc_pot_impl (2853-3265) ----------------------------------
@@ -375,7 +380,10 @@ public:
         p.eps2 = eps2;
         p.G = G;
         p.perm = ordered ? m_b.perm.p : nullptr;
-        m_group_cost.reserve(C, 1.1);
+        if (!m_costs_valid) {
+            m_group_cost.reserve(C, 1.1);
+            RK_CUDA_CHECK(cudaMemsetAsync(m_group_cost.p, 0, C * sizeof(u64), m_stream));
+        }
         p.group_cost = m_group_cost.p;
         p.counters = reinterpret_cast<u64 *>(m_counters.p);
         u32 tmax = static_cast<u32>((std::min<size_t>(m_max_group, 256) + 31) / 32 * 32);
@@ -427,7 +435,7 @@ public:
         if (hw[1]) {
             throw api_error(RK_ERR_RUNTIME, "Traversal stack overflow in the CUDA kernel");
         }
-        m_costs_valid = !partial;
+        m_costs_valid = true; // groups outside the evaluated ranges hold 0
         if (info) {
             info->mac_tests = m_hpin[0];
             info->accepted = m_hpin[1];
@@ -915,6 +923,37 @@ int rk_tree_acc_pot_range(rk_tree *t, int Q, int ordered, double theta, double G
 int rk_tree_exact(rk_tree *t, size_t idx, int ordered, double G, double eps, double out4[4])
 {
     return guarded(t, [&]() { RK_WITH(t, T.exact(idx, ordered != 0, G, eps, out4)); });
+}
+
+const void *rk_tree_group_costs_device(rk_tree *t)
+{
+    if (!t) {
+        return nullptr;
+    }
+    return t->fp == 32 ? t->t32->group_costs_device() : t->t64->group_costs_device();
+}
+
+unsigned long long rk_kernel_launch_count(void)
+{
+    return __atomic_load_n(&rk::g_kernel_launches, __ATOMIC_RELAXED);
+}
+
+int rk_measure_fp32_peak(int device, double *tflops, double *ms)
+{
+    try {
+        RK_CUDA_CHECK(cudaSetDevice(device));
+        float t = 0;
+        const double flops = rk::ffma_microbench(&t);
+        if (tflops) {
+            *tflops = flops / (double(t) * 1e-3) / 1e12;
+        }
+        if (ms) {
+            *ms = t;
+        }
+        return RK_OK;
+    } catch (...) {
+        return RK_ERR_RUNTIME;
+    }
 }
 
 int rk_traverse_external_tree(int, int, int, void *const[4], const uint64_t *, size_t, const void *, size_t,

@@ -85,6 +85,10 @@ struct cuda_error : std::runtime_error {
         }                                                                                                              \
     } while (0)
 
+// Number of kernels this library has launched (bench.py reports it as gpu_launches).
+extern unsigned long long g_kernel_launches;
+inline void count_launch(unsigned n = 1) { __atomic_fetch_add(&g_kernel_launches, n, __ATOMIC_RELAXED); }
+
 inline unsigned div_up(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
 
 // Grow-only device buffer.
@@ -245,6 +249,8 @@ struct trav_params {
 };
 template <typename F>
 void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cudaStream_t st);
+// FFMA-bound microbenchmark on the current device: returns the flop count, *ms the CUDA-event time.
+double ffma_microbench(float *ms);
 template <typename F>
 void launch_exact(const vec4<F> *parts, size_t n, size_t idx, F G, F eps2, double *d_out4, cudaStream_t st);
 

@@ -141,7 +141,7 @@ __global__ void iota_kernel(u32 *p, size_t n)
 void launch_iota(u32 *p, size_t n, cudaStream_t st)
 {
     if (n) {
-        iota_kernel<<<div_up(n, 256), 256, 0, st>>>(p, n);
+        iota_kernel<<<div_up(n, 256), 256, 0, st>>>(p, n); count_launch();
     }
 }
 
@@ -161,7 +161,7 @@ int radix_sort_pairs(u64 *keys_a, u64 *keys_b, u32 *idx_a, u32 *idx_b, size_t n,
     }
     u64 *d_or = reinterpret_cast<u64 *>(sc.ghist.p + 256); // 8-byte aligned: cudaMalloc base + 1024 B
     RK_CUDA_CHECK(cudaMemsetAsync(d_or, 0, sizeof(u64), st));
-    key_or_kernel<<<592, 256, 0, st>>>(keys_a, n, d_or);
+    key_or_kernel<<<592, 256, 0, st>>>(keys_a, n, d_or); count_launch();
     RK_CUDA_CHECK(cudaMemcpyAsync(sc.h_ghist, d_or, sizeof(u64), cudaMemcpyDeviceToHost, st));
     RK_CUDA_CHECK(cudaStreamSynchronize(st));
     u64 varying;
@@ -176,10 +176,10 @@ int radix_sort_pairs(u64 *keys_a, u64 *keys_b, u32 *idx_a, u32 *idx_b, size_t n,
         if (((varying >> shift) & 0xffull) == 0) {
             continue;
         }
-        tile_hist_kernel<<<ntiles, SORT_THREADS, 0, st>>>(kin, n, shift, ntiles, sc.tilehist.p);
-        row_scan_kernel<<<256, 256, 0, st>>>(sc.tilehist.p, ntiles, sc.ghist.p);
+        tile_hist_kernel<<<ntiles, SORT_THREADS, 0, st>>>(kin, n, shift, ntiles, sc.tilehist.p); count_launch();
+        row_scan_kernel<<<256, 256, 0, st>>>(sc.tilehist.p, ntiles, sc.ghist.p); count_launch();
         scatter_kernel<<<ntiles, SORT_THREADS, 0, st>>>(kin, iin, kout, iout, n, shift, ntiles, sc.tilehist.p,
-                                                        sc.ghist.p);
+                                                        sc.ghist.p); count_launch();
         ++passes;
         u64 *tk = kin;
         kin = kout;

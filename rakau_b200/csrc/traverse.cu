@@ -458,6 +458,29 @@ __global__ void __launch_bounds__(1024) exact_kernel(const vec4<F> *__restrict__
     }
 }
 
+// FP32-pipe peak probe: 8 independent FFMA chains per thread, full occupancy.
+__global__ void __launch_bounds__(256) ffma_kernel(float *out, int iters, float a, float b)
+{
+    float v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            v0 = fmaf(v0, a, b);
+            v1 = fmaf(v1, a, b);
+            v2 = fmaf(v2, a, b);
+            v3 = fmaf(v3, a, b);
+            v4 = fmaf(v4, a, b);
+            v5 = fmaf(v5, a, b);
+            v6 = fmaf(v6, a, b);
+            v7 = fmaf(v7, a, b);
+        }
+    }
+    const float s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    if (s == 123.456f) {
+        out[0] = s;
+    }
+}
+
 template <typename F, int Q, int MAC>
 void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st)
 {
@@ -479,7 +502,7 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st)
     if (grid == 0) {
         return;
     }
-    traverse_kernel<F, Q, MAC><<<grid, TRAV_THREADS, smem, st>>>(p);
+    traverse_kernel<F, Q, MAC><<<grid, TRAV_THREADS, smem, st>>>(p); count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -503,10 +526,33 @@ void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cuda
     throw cuda_error(1, "invalid Q / MAC combination");
 }
 
+double ffma_microbench(float *ms)
+{
+    int dev = 0, sms = 0;
+    RK_CUDA_CHECK(cudaGetDevice(&dev));
+    RK_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float *d = nullptr;
+    RK_CUDA_CHECK(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    RK_CUDA_CHECK(cudaEventCreate(&e0));
+    RK_CUDA_CHECK(cudaEventCreate(&e1));
+    const int iters = 4096, grid = sms * 8;
+    ffma_kernel<<<grid, 256>>>(d, 64, 1.0001f, 0.5f); // warm-up
+    RK_CUDA_CHECK(cudaEventRecord(e0));
+    ffma_kernel<<<grid, 256>>>(d, iters, 1.0001f, 0.5f);
+    RK_CUDA_CHECK(cudaEventRecord(e1));
+    RK_CUDA_CHECK(cudaEventSynchronize(e1));
+    RK_CUDA_CHECK(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return 2.0 * 8 * 16 * double(iters) * 256.0 * grid;
+}
+
 template <typename F>
 void launch_exact(const vec4<F> *parts, size_t n, size_t idx, F G, F eps2, double *d_out4, cudaStream_t st)
 {
-    exact_kernel<F><<<1, 1024, 0, st>>>(parts, n, idx, G, eps2, d_out4);
+    exact_kernel<F><<<1, 1024, 0, st>>>(parts, n, idx, G, eps2, d_out4); count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -1,0 +1,151 @@
+"""GPU build (Morton encode, radix sort, octree topology, node properties, critical nodes) vs the oracle,
+through the C ABI. Bit-exact for codes / permutations / topology; stated tolerance for mass and COM
+(the GPU reduces in fp64 with a fixed, mass-independent tree; the reference sums sequentially in F)."""
+import numpy as np
+import pytest
+
+from gpu_util import assert_same_tree, build_pair
+
+pytestmark = pytest.mark.gpu
+
+PROPS_TOL = {32: 2e-5, 64: 1e-12}
+
+
+@pytest.mark.parametrize("N", [1, 2, 33, 1000, 20000])
+@pytest.mark.parametrize("mln,nc", [(1, 1), (16, 128), (8, 4), (3, 1000)])
+def test_plummer_fp32(oracle_mod, rk, N, mln, nc):
+    m, x, y, z = oracle_mod.plummer(N)
+    o, g = build_pair(oracle_mod, rk, x, y, z, m, max_leaf_n=mln, ncrit=nc)
+    assert_same_tree(o, g, PROPS_TOL[32])
+
+
+@pytest.mark.parametrize("fp", [32, 64])
+@pytest.mark.parametrize("mac", ["bh", "bh_geom"])
+def test_uniform_types_and_macs(oracle_mod, rk, fp, mac):
+    m, x, y, z = oracle_mod.Rng(7).uniform_particles(30000, 1.0, fp=fp)
+    o, g = build_pair(oracle_mod, rk, x, y, z, m, fp=fp, mac=mac, box_size=1.25)
+    assert_same_tree(o, g, PROPS_TOL[fp])
+    if mac == "bh_geom":
+        gn, on = g.nodes(), o.nodes()
+        assert np.abs(gn["delta"].astype(np.float64) - on["delta"]).max() <= PROPS_TOL[fp] * o.box_size
+
+
+def test_large_fp32(oracle_mod, rk):
+    m, x, y, z = oracle_mod.plummer(400000)
+    o, g = build_pair(oracle_mod, rk, x, y, z, m)
+    assert_same_tree(o, g, PROPS_TOL[32])
+
+
+def test_duplicates_and_ties(oracle_mod, rk):
+    """Identical positions reach level 21 (leaf larger than max_leaf_n); equal codes keep input order (stable)."""
+    rng = np.random.default_rng(1)
+    N = 5000
+    x, y, z = (rng.normal(size=N).astype(np.float32) for _ in range(3))
+    x[:700], y[:700], z[:700] = x[0], y[0], z[0]
+    x[900:1000] = x[900] + 1e-7
+    for mln, nc in ((1, 1), (16, 128), (8, 600)):
+        o, g = build_pair(oracle_mod, rk, x, y, z, np.ones(N), box_size=20.0, max_leaf_n=mln, ncrit=nc)
+        assert_same_tree(o, g, PROPS_TOL[32])
+        codes = g.codes()
+        assert (codes[1:] == codes[:-1]).sum() >= 699
+        p = g.perm(0).astype(np.int64)
+        same = codes[1:] == codes[:-1]
+        assert (p[1:][same] > p[:-1][same]).all()  # stability
+
+
+def test_all_identical_particles(oracle_mod, rk):
+    N = 300
+    x = np.full(N, 0.25, dtype=np.float32)
+    o, g = build_pair(oracle_mod, rk, x, x, x, np.ones(N), box_size=2.0)
+    assert_same_tree(o, g, PROPS_TOL[32])
+    assert (g.perm(0) == np.arange(N)).all()
+
+
+def test_empty_tree(rk):
+    g = rk.Octree()
+    e = np.zeros(0, dtype=np.float32)
+    g.build(e, e, e, e)
+    assert g.nparts == 0 and g.nnodes == 0 and g.ncrit_nodes == 0
+    assert g.acc_pot(0, 0.75)[0].size == 0
+
+
+def test_kat_node_centre_and_box(oracle_mod, rk):
+    # reference test/node_centre.cpp:55-110 and test/basic.cpp:144-147 through the GPU path
+    x = np.array([1, 1, 1, 1, -1, -1, -1, -1.0])
+    y = np.array([1, 1, -1, -1, 1, 1, -1, -1.0])
+    z = np.array([1, -1, 1, -1, 1, -1, 1, -1.0])
+    for fp in (32, 64):
+        g = rk.Octree(fp=fp)
+        g.build(x, y, z, np.ones(8), box_size=10, max_leaf_n=1, ncrit=1)
+        nd = g.nodes()
+        assert len(nd) == 9 and nd[0]["n_children"] == 8
+        exp = [(-1, -1, -1), (1, -1, -1), (-1, 1, -1), (1, 1, -1), (-1, -1, 1), (1, -1, 1), (-1, 1, 1), (1, 1, 1)]
+        for i, e in enumerate(exp):
+            assert nd[i + 1]["code"] == 8 + i and tuple(nd[i + 1]["props"][:3]) == e
+        c = np.array([-10, 1, 2, 10.0])
+        g.build(c, c, c, np.ones(4))
+        assert g.box_size == 21.0
+        g.build([0, 1, 2, 3], [-4, -5, -6, -7], [4, 5, 3, 1], np.ones(4), max_leaf_n=1, ncrit=1)
+        assert g.F(g.box_size) == g.F(14) + g.F(0.7)  # test/auto_box_size.cpp:34-44
+
+
+@pytest.mark.parametrize("fp", [32, 64])
+def test_constructor_errors(rk, fp):
+    # message substrings of test/basic.cpp:178-202; status codes map to the reference's exception types
+    c = np.array([-10, 1, 2, 10.0])
+    m = np.ones(4)
+    g = rk.Octree(fp=fp)
+
+    def err(**kw):
+        with pytest.raises(rk.RakauError) as e:
+            g.build(c, c, c, m, **kw)
+        assert e.value.status == 1
+        assert g.nparts == 0
+        return str(e.value)
+    assert "produced the floating-point value" in err(box_size=3, max_leaf_n=4, ncrit=5)
+    assert "The box size must be a finite non-negative value, but it is" in err(box_size=-3)
+    assert "The box size must be a finite non-negative value, but it is" in err(box_size=np.inf)
+    assert "The maximum number of particles per leaf must be nonzero" in err(max_leaf_n=0, ncrit=5)
+    assert "The critical number of particles for the vectorised computation of the" in err(max_leaf_n=4, ncrit=0)
+    bad = c.copy()
+    bad[2] = np.nan
+    with pytest.raises(rk.RakauError) as e:
+        g.build(bad, c, c, m)
+    assert "non-finite coordinate" in str(e.value)
+    with pytest.raises(rk.RakauError) as e:
+        g.build(bad, c, c, m, box_size=100.0)
+    assert "While trying to discretise the input coordinate" in str(e.value)
+    with pytest.raises(rk.RakauError) as e:
+        g.build(c, c, c, np.array([1, np.inf, 1, 1.0]), box_size=100.0)
+    assert "non-finite" in str(e.value)
+
+
+def test_full_size_properties(oracle_mod, rk):
+    """BASELINE config 1 size (4M): size-independent invariants instead of an oracle comparison."""
+    N = 4_000_000
+    m, x, y, z = oracle_mod.plummer(N)
+    g = rk.Octree()
+    g.build(x, y, z, m)
+    codes = g.codes()
+    assert (codes[1:] >= codes[:-1]).all()
+    p = g.perm(0).astype(np.int64)
+    assert (np.sort(p) == np.arange(N)).all()
+    assert (g.perm(2)[p] == np.arange(N)).all()
+    px, py, pz, pm = g.parts()
+    assert (px == x[p]).all() and (pm == m[p]).all()
+    nd = g.nodes()
+    assert nd[0]["begin"] == 0 and nd[0]["end"] == N and nd[0]["n_children"] == len(nd) - 1
+    assert ((nd["end"] - nd["begin"]) > 0).all()
+    leaves = nd[nd["n_children"] == 0]
+    assert (leaves["begin"][1:] == leaves["end"][:-1]).all() and leaves["end"][-1] == N  # leaves tile the particles
+    assert ((leaves["end"] - leaves["begin"] <= 16) | (leaves["level"] == 21)).all()
+    cr = g.crit()
+    assert cr[0, 1] == 0 and cr[-1, 2] == N and (cr[1:, 1] == cr[:-1, 2]).all()
+    assert abs(nd[0]["props"][3] / m.astype(np.float64).sum() - 1) < 1e-6
+    # every node's code is the common prefix of its particles' codes
+    lvl = nd["level"].astype(np.uint64)
+    sh = (np.uint64(3) * (np.uint64(21) - lvl))
+    first = codes[nd["begin"]] >> sh
+    last = codes[nd["end"] - np.uint64(1)] >> sh
+    want = nd["code"] - (np.uint64(1) << (np.uint64(3) * lvl))
+    assert (first == want).all() and (last == want).all()
