@@ -17,6 +17,14 @@
 // register-resident targets: broadcast LDS.128 per source, 3 FADD + 3 FFMA + MUFU.RSQ + 3 FMUL + 3 FFMA per
 // pair. Accumulation order is fixed by the tree, not by scheduling, so results are run-to-run
 // deterministic and G enters as one final multiply (reference test g_constant_acc.cpp:65-88).
+//
+// Two refinements found with ncu (profiles/r01_traverse_v1_*): (1) the per-target MAC loop was 26 % of all
+// issued instructions, so each lane first brackets the group MAC with the group's bounding box — if even the
+// nearest point of the box passes (or even the farthest fails) the decision is the reference's, exactly, and
+// the loop is skipped; only nodes inside the ~1e-6-wide guard band run the exact per-target loop;
+// (2) groups average 38 targets, so a warp is cut into S = 32/P slices of P lanes (P = 8, 16, 32 chosen per
+// group to minimise ceil(T/P)*P): every slice holds all targets (R per lane) and evaluates every S-th source,
+// partial sums are combined with a fixed shuffle tree at the end (lane utilisation 73 % -> 90 %).
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -27,15 +35,10 @@ namespace rk
 namespace
 {
 
-constexpr int TRAV_WARPS = 8;
+constexpr int TRAV_WARPS = 4;
 constexpr int TRAV_THREADS = TRAV_WARPS * 32;
-// targets per lane held in registers: 8 (fp32, 256 targets per pass) or 4 (fp64, register budget)
-template <typename F>
-struct trav_cfg {
-    static constexpr int rmax = sizeof(F) == 8 ? 4 : 8;
-};
 constexpr int LCAP = 128;        // source ring capacity (power of two)
-constexpr int STACK_CAP = 1024;  // (first child, count) entries per warp
+constexpr int STACK_CAP = 512;   // (first child, count) entries per warp (<= 32 pushes per step, depth <= 21)
 constexpr u32 FULL = 0xffffffffu;
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
@@ -51,7 +54,14 @@ __device__ __forceinline__ void cp_async_vec4(double4 *dst, const double4 *src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__device__ __forceinline__ float fast_rsqrt(float x) { return rsqrtf(x); }
+// MUFU.RSQ without the denormal pre/post-scaling of rsqrtf() (a squared distance below 1e-38 is not a
+// meaningful input; it flushes to zero exactly like a coincident pair).
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double fast_rsqrt(double x) { return rsqrt(x); }
 
 __device__ __forceinline__ u32 warp_incl_scan(u32 v, int lane)
@@ -87,87 +97,101 @@ __device__ __forceinline__ void interact(const vec4<F> &s, F tx, F ty, F tz, F e
     }
 }
 
-template <typename F, int Q, int RR, int RMAX>
-__device__ __forceinline__ void eval_ring(const vec4<F> *__restrict__ ring, u32 head, u32 cnt, F eps2,
-                                          const F (&tx)[RMAX], const F (&ty)[RMAX], const F (&tz)[RMAX],
-                                          F (&ax)[RMAX], F (&ay)[RMAX], F (&az)[RMAX], F (&ap)[RMAX])
+// Evaluate `cnt` ring sources (every S-th one, starting at sl) against a register tile of W targets whose
+// positions come from the staged target array and whose accumulators live in shared memory between batches
+// (one float4/double4 per (slot, lane): conflict-free LDS.128/STS.128). Keeping only W <= 4 slots in registers
+// keeps the kernel small enough for the instruction cache: the first version unrolled 8 register-resident
+// variants and spent 5.6 issue slots per instruction waiting on instruction fetch (profiles/r01_traverse_v2_*).
+template <typename F, int Q, int W, bool SELF>
+__device__ __forceinline__ void eval_tile(const vec4<F> *__restrict__ src, u32 head, u32 cnt, u32 mask, u32 sl, u32 S,
+                                          F eps2, const vec4<F> *__restrict__ tpos, u32 T, u32 first_t, u32 P,
+                                          vec4<F> *__restrict__ acc)
 {
-#pragma unroll 4
-    for (u32 j = 0; j < cnt; ++j) {
-        const vec4<F> s = ring[(head + j) & (LCAP - 1)];
+    F tx[W], ty[W], tz[W], ax[W], ay[W], az[W], ap[W];
+    u32 self_idx[W];
 #pragma unroll
-        for (int k = 0; k < RR; ++k) {
-            interact<F, Q>(s, tx[k], ty[k], tz[k], eps2, ax[k], ay[k], az[k], ap[k]);
-        }
+    for (int w = 0; w < W; ++w) {
+        const u32 ti = first_t + P * w;
+        const vec4<F> t = tpos[ti < T ? ti : T - 1u];
+        const vec4<F> a = acc[32 * w];
+        tx[w] = t.x;
+        ty[w] = t.y;
+        tz[w] = t.z;
+        ax[w] = a.x;
+        ay[w] = a.y;
+        az[w] = a.z;
+        ap[w] = a.w;
+        self_idx[w] = ti;
     }
-}
-
-// Self interactions: sources are the group's own particles, the (i, i) pair is masked out.
-template <typename F, int Q, int RR, int RMAX>
-__device__ __forceinline__ void eval_self(const vec4<F> *__restrict__ src, u32 T, u32 my0 /* t0 + lane */, F eps2,
-                                          const F (&tx)[RMAX], const F (&ty)[RMAX], const F (&tz)[RMAX],
-                                          F (&ax)[RMAX], F (&ay)[RMAX], F (&az)[RMAX], F (&ap)[RMAX])
-{
 #pragma unroll 2
-    for (u32 j = 0; j < T; ++j) {
-        const vec4<F> s = src[j];
+    for (u32 j = sl; j < cnt; j += S) {
+        const vec4<F> s = src[(head + j) & mask];
 #pragma unroll
-        for (int k = 0; k < RR; ++k) {
-            const F dx = s.x - tx[k], dy = s.y - ty[k], dz = s.z - tz[k];
+        for (int w = 0; w < W; ++w) {
+            const F dx = s.x - tx[w], dy = s.y - ty[w], dz = s.z - tz[w];
             F d2 = fma(dx, dx, eps2);
             d2 = fma(dy, dy, d2);
             d2 = fma(dz, dz, d2);
             F inv = fast_rsqrt(d2);
-            inv = (j == my0 + 32u * k) ? F(0) : inv;
+            if (SELF) {
+                inv = (j == self_idx[w]) ? F(0) : inv; // the (i, i) pair
+            }
             if (Q != 1) {
                 const F ms = s.w * (inv * inv * inv);
-                ax[k] = fma(dx, ms, ax[k]);
-                ay[k] = fma(dy, ms, ay[k]);
-                az[k] = fma(dz, ms, az[k]);
+                ax[w] = fma(dx, ms, ax[w]);
+                ay[w] = fma(dy, ms, ay[w]);
+                az[w] = fma(dz, ms, az[w]);
             }
             if (Q != 0) {
-                ap[k] = fma(s.w, inv, ap[k]);
+                ap[w] = fma(s.w, inv, ap[w]);
             }
         }
     }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        acc[32 * w] = make_vec4<F>(ax[w], ay[w], az[w], ap[w]);
+    }
 }
 
-#define RK_RR_CASE(N, CALL)                                                                                            \
-    case N:                                                                                                            \
-        if constexpr (N <= RMAX) {                                                                                     \
-            CALL(N);                                                                                                   \
-        }                                                                                                              \
-        break;
-#define RK_RR_SWITCH(rr, CALL)                                                                                         \
-    switch (rr) {                                                                                                      \
-        RK_RR_CASE(1, CALL)                                                                                            \
-        RK_RR_CASE(2, CALL)                                                                                            \
-        RK_RR_CASE(3, CALL)                                                                                            \
-        RK_RR_CASE(4, CALL)                                                                                            \
-        RK_RR_CASE(5, CALL)                                                                                            \
-        RK_RR_CASE(6, CALL)                                                                                            \
-        RK_RR_CASE(7, CALL)                                                                                            \
-        RK_RR_CASE(8, CALL)                                                                                            \
-        default: break;                                                                                                \
+// All rr slots of this lane against the same sources: tiles of 4, 2, 1 slots.
+template <typename F, int Q, bool SELF>
+__device__ __forceinline__ void eval_slots(const vec4<F> *__restrict__ src, u32 head, u32 cnt, u32 mask, u32 sl, u32 S,
+                                           F eps2, const vec4<F> *__restrict__ tpos, u32 T, u32 t_lane, u32 P, u32 rr,
+                                           vec4<F> *__restrict__ acc_lane)
+{
+    u32 k = 0;
+#pragma unroll 1
+    for (; k + 4u <= rr; k += 4u) {
+        eval_tile<F, Q, 4, SELF>(src, head, cnt, mask, sl, S, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
     }
+    if (k + 2u <= rr) {
+        eval_tile<F, Q, 2, SELF>(src, head, cnt, mask, sl, S, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        k += 2u;
+    }
+    if (k < rr) {
+        eval_tile<F, Q, 1, SELF>(src, head, cnt, mask, sl, S, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+    }
+}
 
 template <typename F>
 __host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax)
 {
-    return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(STACK_CAP) * 4 + 32 * 4 /*nodebuf*/
-           + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
+    // ring + staged targets + accumulators (2 * tmax entries: up to 2*tmax/32 slots per lane) + stack + small queues
+    return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(2 * tmax) * sizeof(vec4<F>)
+           + size_t(STACK_CAP) * 4 + 32 * 4 /*nodebuf*/ + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
 }
 
 template <typename F, int Q, int MAC>
-__global__ void __launch_bounds__(TRAV_THREADS, 2) traverse_kernel(const trav_params<F> p)
+__global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_params<F> p)
 {
-    constexpr int RMAX = trav_cfg<F>::rmax;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *base = smem_raw + size_t(warp) * warp_smem_bytes<F>(p.tmax);
     vec4<F> *ring = reinterpret_cast<vec4<F> *>(base);
     vec4<F> *tgt = ring + LCAP;
-    u32 *stack = reinterpret_cast<u32 *>(tgt + p.tmax);
+    vec4<F> *acc = tgt + p.tmax;
+    u32 *stack = reinterpret_cast<u32 *>(acc + 2 * p.tmax);
+    const u32 rr_cap = 2u * p.tmax / 32u; // accumulator slots per lane
     u32 *nodebuf = stack + STACK_CAP;
     u32 *lq_incl = nodebuf + 32;
     u32 *lq_base = lq_incl + 32;
@@ -185,35 +209,68 @@ __global__ void __launch_bounds__(TRAV_THREADS, 2) traverse_kernel(const trav_pa
         }
         const u32 gnode = p.crit_node[g], gb = p.crit_begin[g], ge = p.crit_begin[g + 1], T = ge - gb;
         const bool staged = T <= p.tmax;
-        const vec4<F> *tsrc = staged ? tgt : (p.parts + gb);
+        const vec4<F> *gsrc = p.parts + gb;
         __syncwarp();
-        if (staged) {
+        // Stage the targets (MAC test + self interactions) and compute the group's bounding box.
+        F blo[3], bhi[3];
+        {
+            F lo0 = F(INFINITY), lo1 = F(INFINITY), lo2 = F(INFINITY), hi0 = -F(INFINITY), hi1 = -F(INFINITY),
+              hi2 = -F(INFINITY);
             for (u32 i = lane; i < T; i += 32) {
-                tgt[i] = p.parts[gb + i];
+                const vec4<F> v = gsrc[i];
+                if (staged) {
+                    tgt[i] = v;
+                }
+                lo0 = fmin(lo0, v.x);
+                hi0 = fmax(hi0, v.x);
+                lo1 = fmin(lo1, v.y);
+                hi1 = fmax(hi1, v.y);
+                lo2 = fmin(lo2, v.z);
+                hi2 = fmax(hi2, v.z);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo0 = fmin(lo0, __shfl_xor_sync(FULL, lo0, o));
+                lo1 = fmin(lo1, __shfl_xor_sync(FULL, lo1, o));
+                lo2 = fmin(lo2, __shfl_xor_sync(FULL, lo2, o));
+                hi0 = fmax(hi0, __shfl_xor_sync(FULL, hi0, o));
+                hi1 = fmax(hi1, __shfl_xor_sync(FULL, hi1, o));
+                hi2 = fmax(hi2, __shfl_xor_sync(FULL, hi2, o));
+            }
+            blo[0] = lo0;
+            blo[1] = lo1;
+            blo[2] = lo2;
+            bhi[0] = hi0;
+            bhi[1] = hi1;
+            bhi[2] = hi2;
         }
         __syncwarp();
 
         u64 n_mac = 0, n_acc = 0, n_p2p = 0; // warp-uniform counters
+        u64 dbg_need = 0, dbg_steps = 0, dbg_needsteps = 0;
 
-        // Groups larger than 32*RMAX targets are handled in several passes, each repeating the traversal
-        // (the MAC always spans the whole group, as in the reference).
-        for (u32 t0 = 0; t0 < T; t0 += 32u * RMAX) {
-            const u32 tc = (T - t0 < 32u * RMAX) ? (T - t0) : 32u * RMAX;
-            const int rr = static_cast<int>((tc + 31u) / 32u);
-            F tx[RMAX], ty[RMAX], tz[RMAX], tm[RMAX], ax[RMAX], ay[RMAX], az[RMAX], ap[RMAX];
-#pragma unroll
-            for (int k = 0; k < RMAX; ++k) {
-                const u32 i = t0 + 32u * k + lane;
-                vec4<F> v = make_vec4<F>(F(0), F(0), F(0), F(0));
-                if (k < rr && i < T) {
-                    v = tsrc[i];
+        // Groups with more targets than the accumulator array holds are handled in several passes, each
+        // repeating the traversal (the MAC always spans the whole group, as in the reference).
+        const vec4<F> *tpos = staged ? tgt : gsrc;
+        for (u32 t0 = 0; t0 < T; t0 += 32u * rr_cap) {
+            const u32 tc = (T - t0 < 32u * rr_cap) ? (T - t0) : 32u * rr_cap;
+            // Slice the warp: P lanes per slice, S = 32/P slices, rr target slots per lane; minimise rr * P >= tc.
+            u32 P = 32u, rr = (tc + 31u) / 32u;
+            {
+                const u32 r16 = (tc + 15u) / 16u, r8 = (tc + 7u) / 8u;
+                if (r16 <= rr_cap && r16 * 16u < rr * P) {
+                    P = 16u;
+                    rr = r16;
                 }
-                tx[k] = v.x;
-                ty[k] = v.y;
-                tz[k] = v.z;
-                tm[k] = v.w;
-                ax[k] = ay[k] = az[k] = ap[k] = F(0);
+                if (r8 <= rr_cap && r8 * 8u < rr * P) {
+                    P = 8u;
+                    rr = r8;
+                }
+            }
+            const u32 S = 32u / P, sl = static_cast<u32>(lane) / P, tl = static_cast<u32>(lane) % P;
+            vec4<F> *acc_lane = acc + lane;
+            for (u32 k = 0; k < rr; ++k) {
+                acc_lane[32u * k] = make_vec4<F>(F(0), F(0), F(0), F(0));
             }
 
             u32 sp = 1, lhead = 0, lcount = 0, lq_total = 0, lq_done = 0;
@@ -301,22 +358,62 @@ __global__ void __launch_bounds__(TRAV_THREADS, 2) traverse_kernel(const trav_pa
                             mac_lh = rn_mul(t, t);
                         }
                     }
-                    // Group MAC, tree.hpp:2741-2759: fails as soon as one target has mac_lh >= dist2.
-                    bool fail = !test;
-                    for (u32 i = 0; i < T; ++i) {
-                        const vec4<F> t = tsrc[i];
-                        const F dx = rn_sub(na.x, t.x), dy = rn_sub(na.y, t.y), dz = rn_sub(na.z, t.z);
-                        F d2 = rn_mul(dx, dx);
-                        d2 = rn_fma(dy, dy, d2);
-                        d2 = rn_fma(dz, dz, d2);
-                        fail = fail || (mac_lh >= d2);
-                        if ((i & 3u) == 3u && __all_sync(FULL, fail)) {
-                            break;
+                    // Group MAC, tree.hpp:2741-2759: the node is accepted iff mac_lh < dist2 for EVERY target.
+                    // Bracket min/max dist2 over the group with its bounding box first: outside a guard band of
+                    // 2^-20 (>> the 8 eps rounding spread of the two evaluations) the decision is already the
+                    // reference's and the exact loop is skipped.
+                    bool sure_acc = false, sure_rej = false;
+                    if (test) {
+                        F dmin2 = F(0), dmax2 = F(0);
+                        const F c[3] = {na.x, na.y, na.z};
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const F a = blo[j] - c[j], b = c[j] - bhi[j];
+                            const F gap = fmax(F(0), fmax(a, b)), far = fmax(-a, -b);
+                            dmin2 = fma(gap, gap, dmin2);
+                            dmax2 = fma(far, far, dmax2);
+                        }
+                        sure_acc = mac_lh < dmin2 * (F(1) - F(9.5367431640625e-07));
+                        sure_rej = mac_lh >= dmax2 * (F(1) + F(9.5367431640625e-07));
+                    }
+                    const bool need = test && !sure_acc && !sure_rej;
+                    bool fail = !need;
+                    { const u32 mn = __ballot_sync(FULL, need); dbg_need += __popc(mn); dbg_steps += 1; dbg_needsteps += mn ? 1 : 0; }
+                    if (__any_sync(FULL, need)) {
+                        if (staged) {
+                            for (u32 i = 0; i < T; i += 4) {
+#pragma unroll
+                                for (u32 u = 0; u < 4; ++u) {
+                                    // entries past T repeat the last target (tmax is a multiple of 32 >= T)
+                                    const vec4<F> t = tgt[(i + u < T) ? (i + u) : (T - 1u)];
+                                    const F dx = rn_sub(na.x, t.x), dy = rn_sub(na.y, t.y), dz = rn_sub(na.z, t.z);
+                                    F d2 = rn_mul(dx, dx);
+                                    d2 = rn_fma(dy, dy, d2);
+                                    d2 = rn_fma(dz, dz, d2);
+                                    fail = fail || (mac_lh >= d2);
+                                }
+                                if (__all_sync(FULL, fail)) {
+                                    break;
+                                }
+                            }
+                        } else {
+                            for (u32 i = 0; i < T; ++i) {
+                                const vec4<F> t = gsrc[i];
+                                const F dx = rn_sub(na.x, t.x), dy = rn_sub(na.y, t.y), dz = rn_sub(na.z, t.z);
+                                F d2 = rn_mul(dx, dx);
+                                d2 = rn_fma(dy, dy, d2);
+                                d2 = rn_fma(dz, dz, d2);
+                                fail = fail || (mac_lh >= d2);
+                                if ((i & 7u) == 7u && __all_sync(FULL, fail)) {
+                                    break;
+                                }
+                            }
                         }
                     }
-                    const bool accept = test && !fail;
-                    const bool open_leaf = test && fail && nch == 0u;
-                    const bool descend = is_anc || (test && fail && nch != 0u);
+                    const bool accept = sure_acc || (need && !fail);
+                    const bool rejected = sure_rej || (need && fail);
+                    const bool open_leaf = rejected && nch == 0u;
+                    const bool descend = is_anc || (rejected && nch != 0u);
                     const u32 m_test = __ballot_sync(FULL, test), m_acc = __ballot_sync(FULL, accept),
                               m_leaf = __ballot_sync(FULL, open_leaf), m_desc = __ballot_sync(FULL, descend);
                     n_mac += __popc(m_test);
@@ -356,9 +453,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 2) traverse_kernel(const trav_pa
                 }
                 // ---------------- consume: evaluate up to 32 sources (the only ring call site) ----------------
                 const u32 ne = lcount < 32u ? lcount : 32u;
-#define RK_CALL_RING(RR) eval_ring<F, Q, RR, RMAX>(ring, lhead, ne, eps2, tx, ty, tz, ax, ay, az, ap)
-                RK_RR_SWITCH(rr, RK_CALL_RING)
-#undef RK_CALL_RING
+                eval_slots<F, Q, false>(ring, lhead, ne, LCAP - 1, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
                 __syncwarp();
                 lhead = (lhead + ne) & (LCAP - 1);
                 lcount -= ne;
@@ -367,31 +462,41 @@ __global__ void __launch_bounds__(TRAV_THREADS, 2) traverse_kernel(const trav_pa
                 atomicExch(p.err, 1u);
             }
 
-            // self interactions inside the group, tree.hpp:2073-2321
-#define RK_CALL_SELF(RR) eval_self<F, Q, RR, RMAX>(tsrc, T, t0 + lane, eps2, tx, ty, tz, ax, ay, az, ap)
-            RK_RR_SWITCH(rr, RK_CALL_SELF)
-#undef RK_CALL_SELF
+            // self interactions inside the group, tree.hpp:2073-2321 (sources = the group's own particles)
+            if (staged) {
+                eval_slots<F, Q, true>(tgt, 0u, T, 0xffffffffu, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+            } else {
+                eval_slots<F, Q, true>(gsrc, 0u, T, 0xffffffffu, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+            }
 
-            // G scaling (one final multiply, tree.hpp:2986-3002) and write-out (3004-3007)
-#pragma unroll
-            for (int kk = 0; kk < RMAX; ++kk) {
-                const u32 i = t0 + 32u * kk + lane;
-                if (kk < rr && i < T) {
+            // Combine the slices' partial sums (fixed shuffle tree: deterministic), apply G as one final multiply
+            // (tree.hpp:2986-3002) and write out (3004-3007).
+            for (u32 k = 0; k < rr; ++k) {
+                vec4<F> a = acc_lane[32u * k];
+                for (u32 o = P; o < 32u; o <<= 1) {
+                    a.x += __shfl_xor_sync(FULL, a.x, o);
+                    a.y += __shfl_xor_sync(FULL, a.y, o);
+                    a.z += __shfl_xor_sync(FULL, a.z, o);
+                    a.w += __shfl_xor_sync(FULL, a.w, o);
+                }
+                const u32 i = t0 + P * k + tl;
+                if (sl == 0u && i < t0 + tc) {
                     u32 dst = gb + i;
+                    const F tmass = tpos[i].w;
                     if (p.perm) {
                         dst = p.perm[dst];
                     }
                     dst -= p.out_offset;
                     if (Q == 0 || Q == 2) {
-                        p.out[0][dst] = ax[kk] * p.G;
-                        p.out[1][dst] = ay[kk] * p.G;
-                        p.out[2][dst] = az[kk] * p.G;
+                        p.out[0][dst] = a.x * p.G;
+                        p.out[1][dst] = a.y * p.G;
+                        p.out[2][dst] = a.z * p.G;
                     }
                     if (Q == 1) {
-                        p.out[0][dst] = (-tm[kk] * ap[kk]) * p.G;
+                        p.out[0][dst] = (-tmass * a.w) * p.G;
                     }
                     if (Q == 2) {
-                        p.out[3][dst] = (-tm[kk] * ap[kk]) * p.G;
+                        p.out[3][dst] = (-tmass * a.w) * p.G;
                     }
                 }
             }
@@ -405,6 +510,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, 2) traverse_kernel(const trav_pa
                     atomicAdd(p.counters + 2, n_p2p * T);
                     atomicAdd(p.counters + 3, u64(T) * (u64(T) - 1u) / 2u);
                     atomicAdd(p.counters + 4, n_acc * T);
+                    atomicAdd(p.counters + 5, dbg_need);
+                    atomicAdd(p.counters + 6, dbg_steps);
+                    atomicAdd(p.counters + 7, dbg_needsteps);
                 }
             }
             n_mac = n_acc = n_p2p = 0; // count the first pass only

@@ -23,12 +23,19 @@ def assert_same_tree(o, g, props_tol):
     for f in ("begin", "end", "n_children", "code", "level"):
         assert (gn[f] == on[f]).all(), f
     assert (gn["dim"] == on["dim"]).all()  # dim2 / dim: pure function of level and box
-    # mass: relative; COM: absolute error relative to the node size (a COM component can be ~0)
+    # Node properties. The reference sums each node sequentially in F (tree.hpp:1162-1168), the GPU reduces in
+    # fp64 with a fixed tree and rounds once, so the difference is bounded by the REFERENCE's own summation
+    # error: n * eps_F relative for the mass, n * eps_F * (|com| + node size) for each COM component.
+    # props_tol caps the bound for small nodes (a few ulps).
+    cnt = (on["end"] - on["begin"]).astype(np.float64)
+    eps = float(np.finfo(F).eps)
+    bound = np.maximum(props_tol, (cnt + 8.0) * eps)
     mass_err = np.abs(gn["props"][:, 3].astype(np.float64) - on["props"][:, 3]) / np.maximum(np.abs(on["props"][:, 3]), 1e-300)
-    assert mass_err.max() <= props_tol, mass_err.max()
+    assert (mass_err <= bound).all(), (mass_err / bound).max()
     size = o.box_size / (2.0 ** on["level"].astype(np.float64))
-    com_err = np.abs(gn["props"][:, :3].astype(np.float64) - on["props"][:, :3]).max(axis=1) / size
-    assert com_err.max() <= props_tol, com_err.max()
+    scale = np.abs(on["props"][:, :3].astype(np.float64)).max(axis=1) + size
+    com_err = np.abs(gn["props"][:, :3].astype(np.float64) - on["props"][:, :3]).max(axis=1) / scale
+    assert (com_err <= bound).all(), (com_err / bound).max()
     gc, (oc, _) = g.crit(), o.crit()
     assert gc.shape == oc.shape and (gc == oc).all()
 
