@@ -449,7 +449,6 @@ public:
             RK_CUDA_CHECK(cudaEventElapsedTime(&info->ms_total, m_ev.ev[4], m_ev.ev[7]));
             // interactions = sum over groups of T*(leaf sources + accepted) + T*(T-1)
             info->interactions = info->p2p_pairs + 2 * info->self_pairs + m_hpin[4]; // [4] = sum T * accepted
-            if (getenv("RK_DEBUG")) fprintf(stderr, "dbg need=%llu steps=%llu needsteps=%llu\n", m_hpin[5], m_hpin[6], m_hpin[7]);
         }
     }
 

@@ -97,14 +97,14 @@ __device__ __forceinline__ void interact(const vec4<F> &s, F tx, F ty, F tz, F e
     }
 }
 
-// Evaluate `cnt` ring sources (every S-th one, starting at sl) against a register tile of W targets whose
+// Evaluate the sources src[jb, je) (this slice's contiguous share of the batch) against a register tile of W targets whose
 // positions come from the staged target array and whose accumulators live in shared memory between batches
 // (one float4/double4 per (slot, lane): conflict-free LDS.128/STS.128). Keeping only W <= 4 slots in registers
 // keeps the kernel small enough for the instruction cache: the first version unrolled 8 register-resident
 // variants and spent 5.6 issue slots per instruction waiting on instruction fetch (profiles/r01_traverse_v2_*).
 template <typename F, int Q, int W, bool SELF>
-__device__ __forceinline__ void eval_tile(const vec4<F> *__restrict__ src, u32 head, u32 cnt, u32 mask, u32 sl, u32 S,
-                                          F eps2, const vec4<F> *__restrict__ tpos, u32 T, u32 first_t, u32 P,
+__device__ __forceinline__ void eval_tile(const vec4<F> *__restrict__ src, u32 jb, u32 je, F eps2,
+                                          const vec4<F> *__restrict__ tpos, u32 T, u32 first_t, u32 P,
                                           vec4<F> *__restrict__ acc)
 {
     F tx[W], ty[W], tz[W], ax[W], ay[W], az[W], ap[W];
@@ -123,9 +123,9 @@ __device__ __forceinline__ void eval_tile(const vec4<F> *__restrict__ src, u32 h
         ap[w] = a.w;
         self_idx[w] = ti;
     }
-#pragma unroll 2
-    for (u32 j = sl; j < cnt; j += S) {
-        const vec4<F> s = src[(head + j) & mask];
+#pragma unroll 4
+    for (u32 j = jb; j < je; ++j) {
+        const vec4<F> s = src[j];
 #pragma unroll
         for (int w = 0; w < W; ++w) {
             const F dx = s.x - tx[w], dy = s.y - ty[w], dz = s.z - tz[w];
@@ -155,21 +155,23 @@ __device__ __forceinline__ void eval_tile(const vec4<F> *__restrict__ src, u32 h
 
 // All rr slots of this lane against the same sources: tiles of 4, 2, 1 slots.
 template <typename F, int Q, bool SELF>
-__device__ __forceinline__ void eval_slots(const vec4<F> *__restrict__ src, u32 head, u32 cnt, u32 mask, u32 sl, u32 S,
-                                           F eps2, const vec4<F> *__restrict__ tpos, u32 T, u32 t_lane, u32 P, u32 rr,
+__device__ __forceinline__ void eval_slots(const vec4<F> *__restrict__ src, u32 cnt, u32 sl, u32 S, F eps2,
+                                           const vec4<F> *__restrict__ tpos, u32 T, u32 t_lane, u32 P, u32 rr,
                                            vec4<F> *__restrict__ acc_lane)
 {
+    // slice sl takes the contiguous chunk [sl * per, (sl + 1) * per) of the cnt sources
+    const u32 per = (cnt + S - 1u) / S, jb = sl * per < cnt ? sl * per : cnt, je = jb + per < cnt ? jb + per : cnt;
     u32 k = 0;
 #pragma unroll 1
     for (; k + 4u <= rr; k += 4u) {
-        eval_tile<F, Q, 4, SELF>(src, head, cnt, mask, sl, S, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile<F, Q, 4, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
     }
     if (k + 2u <= rr) {
-        eval_tile<F, Q, 2, SELF>(src, head, cnt, mask, sl, S, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile<F, Q, 2, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
         k += 2u;
     }
     if (k < rr) {
-        eval_tile<F, Q, 1, SELF>(src, head, cnt, mask, sl, S, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile<F, Q, 1, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
     }
 }
 
@@ -246,8 +248,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_pa
         }
         __syncwarp();
 
-        u64 n_mac = 0, n_acc = 0, n_p2p = 0; // warp-uniform counters
-        u64 dbg_need = 0, dbg_steps = 0, dbg_needsteps = 0;
+        u32 n_mac = 0, n_acc = 0, n_p2p = 0; // warp-uniform counters (a group visits far fewer than 2^32 nodes)
 
         // Groups with more targets than the accumulator array holds are handled in several passes, each
         // repeating the traversal (the MAC always spans the whole group, as in the reference).
@@ -308,40 +309,24 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_pa
                         done = true;
                         break;
                     }
-                    // ---- pop up to 32 nodes ----
-                    u32 ecnt = 0, efc = 0;
-                    if (static_cast<u32>(lane) < sp) {
-                        const u32 e = stack[sp - 1 - lane];
-                        ecnt = (e & 7u) + 1u;
-                        efc = e >> 3;
+                    // ---- pop up to 4 (first child, count) entries: lane -> entry lane>>3, child lane&7 ----
+                    // (an internal node of the 4M Plummer tree has 7.1 children on average, so this keeps
+                    // ~7/8 of the lanes busy without the prefix scan / expansion buffer an exact 32-node pop needs)
+                    const u32 eidx = static_cast<u32>(lane) >> 3, cidx = static_cast<u32>(lane) & 7u;
+                    bool have = false;
+                    u32 k = 0;
+                    if (eidx < sp) {
+                        const u32 e = stack[sp - 1u - eidx];
+                        have = cidx <= (e & 7u);
+                        k = (e >> 3) + cidx;
                     }
-                    const u32 incl = warp_incl_scan(ecnt, lane), excl = incl - ecnt;
-                    const bool take = ecnt && excl < 32u;
-                    const u32 ntake = __popc(__ballot_sync(FULL, take));
-                    bool partial = false;
-                    if (take) {
-                        const u32 used = (ecnt < 32u - excl) ? ecnt : (32u - excl);
-                        for (u32 t = 0; t < used; ++t) {
-                            nodebuf[excl + t] = efc + t;
-                        }
-                        if (used < ecnt) {
-                            stack[sp - 1 - lane] = ((efc + used) << 3) | (ecnt - used - 1u);
-                            partial = true;
-                        }
-                    }
-                    const bool any_partial = __any_sync(FULL, partial);
-                    u32 nnodes = __shfl_sync(FULL, incl, ntake - 1);
-                    nnodes = nnodes < 32u ? nnodes : 32u;
-                    sp -= ntake - (any_partial ? 1u : 0u);
+                    sp -= sp < 4u ? sp : 4u;
                     __syncwarp();
 
                     // ---- one node per lane: classify ----
-                    const bool have = static_cast<u32>(lane) < nnodes;
-                    u32 k = 0;
                     uint4 nb = make_uint4(0, 0, 0, 0);
                     vec4<F> na = make_vec4<F>(F(0), F(0), F(0), F(0));
                     if (have) {
-                        k = nodebuf[lane];
                         nb = p.nodeB[k];
                         na = p.nodeA[k];
                     }
@@ -378,23 +363,36 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_pa
                     }
                     const bool need = test && !sure_acc && !sure_rej;
                     bool fail = !need;
-                    { const u32 mn = __ballot_sync(FULL, need); dbg_need += __popc(mn); dbg_steps += 1; dbg_needsteps += mn ? 1 : 0; }
                     if (__any_sync(FULL, need)) {
                         if (staged) {
-                            for (u32 i = 0; i < T; i += 4) {
-#pragma unroll
-                                for (u32 u = 0; u < 4; ++u) {
-                                    // entries past T repeat the last target (tmax is a multiple of 32 >= T)
-                                    const vec4<F> t = tgt[(i + u < T) ? (i + u) : (T - 1u)];
-                                    const F dx = rn_sub(na.x, t.x), dy = rn_sub(na.y, t.y), dz = rn_sub(na.z, t.z);
+                            // cooperative: the ambiguous nodes are compacted into shared memory (com, mac_lh) and
+                            // the 32 lanes share the targets of ONE node at a time (broadcast LDS.128 per node)
+                            const u32 m_need = __ballot_sync(FULL, need);
+                            const u32 n_need = __popc(m_need), my_slot = __popc(m_need & ltm);
+                            vec4<F> *amb = ring + ((lhead + 32u) & (LCAP - 1)); // a free 32-entry block (lcount < 32 here)
+                            if (need) {
+                                amb[my_slot] = make_vec4<F>(na.x, na.y, na.z, mac_lh);
+                            }
+                            __syncwarp();
+                            u32 fail_bits = 0;
+#pragma unroll 1
+                            for (u32 a = 0; a < n_need; ++a) {
+                                const vec4<F> c = amb[a];
+                                bool f = false;
+#pragma unroll 1
+                                for (u32 i = lane; i < T; i += 32) {
+                                    const vec4<F> t = tgt[i];
+                                    const F dx = rn_sub(c.x, t.x), dy = rn_sub(c.y, t.y), dz = rn_sub(c.z, t.z);
                                     F d2 = rn_mul(dx, dx);
                                     d2 = rn_fma(dy, dy, d2);
                                     d2 = rn_fma(dz, dz, d2);
-                                    fail = fail || (mac_lh >= d2);
+                                    f = f || (c.w >= d2);
                                 }
-                                if (__all_sync(FULL, fail)) {
-                                    break;
-                                }
+                                fail_bits |= __any_sync(FULL, f) ? (1u << a) : 0u;
+                            }
+                            __syncwarp();
+                            if (need) {
+                                fail = (fail_bits >> my_slot) & 1u;
                             }
                         } else {
                             for (u32 i = 0; i < T; ++i) {
@@ -453,7 +451,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_pa
                 }
                 // ---------------- consume: evaluate up to 32 sources (the only ring call site) ----------------
                 const u32 ne = lcount < 32u ? lcount : 32u;
-                eval_slots<F, Q, false>(ring, lhead, ne, LCAP - 1, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                eval_slots<F, Q, false>(ring + lhead, ne, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
                 __syncwarp();
                 lhead = (lhead + ne) & (LCAP - 1);
                 lcount -= ne;
@@ -464,9 +462,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_pa
 
             // self interactions inside the group, tree.hpp:2073-2321 (sources = the group's own particles)
             if (staged) {
-                eval_slots<F, Q, true>(tgt, 0u, T, 0xffffffffu, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                eval_slots<F, Q, true>(tgt, T, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
             } else {
-                eval_slots<F, Q, true>(gsrc, 0u, T, 0xffffffffu, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                eval_slots<F, Q, true>(gsrc, T, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
             }
 
             // Combine the slices' partial sums (fixed shuffle tree: deterministic), apply G as one final multiply
@@ -502,17 +500,14 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_pa
             }
             if (t0 == 0 && lane == 0) {
                 if (p.group_cost) {
-                    p.group_cost[g] = u64(T) * (n_p2p + n_acc + u64(T) - 1u);
+                    p.group_cost[g] = u64(T) * (u64(n_p2p) + n_acc + u64(T) - 1u);
                 }
                 if (p.counters) {
-                    atomicAdd(p.counters + 0, n_mac);
-                    atomicAdd(p.counters + 1, n_acc);
-                    atomicAdd(p.counters + 2, n_p2p * T);
+                    atomicAdd(p.counters + 0, u64(n_mac));
+                    atomicAdd(p.counters + 1, u64(n_acc));
+                    atomicAdd(p.counters + 2, u64(n_p2p) * T);
                     atomicAdd(p.counters + 3, u64(T) * (u64(T) - 1u) / 2u);
-                    atomicAdd(p.counters + 4, n_acc * T);
-                    atomicAdd(p.counters + 5, dbg_need);
-                    atomicAdd(p.counters + 6, dbg_steps);
-                    atomicAdd(p.counters + 7, dbg_needsteps);
+                    atomicAdd(p.counters + 4, u64(n_acc) * T);
                 }
             }
             n_mac = n_acc = n_p2p = 0; // count the first pass only
