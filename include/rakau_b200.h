@@ -109,11 +109,15 @@ RK_API int rk_tree_synchronize(rk_tree *t);
  * 1116-1237). */
 RK_API int rk_tree_build(rk_tree *t, const void *x, const void *y, const void *z, const void *m, size_t n, int where,
                          double box_size, int deduce_box, size_t max_leaf_n, size_t ncrit, rk_build_info *info);
-/* sync(), tree.hpp:3678-3743: new coordinates in the CURRENT Morton order (NULL = unchanged). */
-RK_API int rk_tree_update_positions(rk_tree *t, const void *x, const void *y, const void *z, int where,
+/* sync(), tree.hpp:3678-3743: new coordinates and masses in the CURRENT Morton order (NULL = unchanged), as left
+ * behind by the update_particles_u functor (tree.hpp:3746-3765). */
+RK_API int rk_tree_update_positions(rk_tree *t, const void *x, const void *y, const void *z, const void *m, int where,
                                     rk_build_info *info);
 /* update_masses_dispatch, tree.hpp:3782-3805: new masses in the current Morton order; topology untouched. */
 RK_API int rk_tree_update_masses(rk_tree *t, const void *m, int where);
+/* Copy constructor / assignment (tree.hpp:1735-1743, 1785-1822): deep device-to-device copy of src into dst
+ * (same fp_bits and mac). */
+RK_API int rk_tree_clone(rk_tree *dst, const rk_tree *src);
 /* clear(), tree.hpp:1882-1904. */
 RK_API int rk_tree_clear(rk_tree *t);
 

@@ -33,7 +33,7 @@ SYMBOLS = [
     "rk_tree_box_size", "rk_tree_get_parts", "rk_tree_get_codes", "rk_tree_get_perm", "rk_tree_get_nodes",
     "rk_tree_get_crit", "rk_tree_acc_pot", "rk_tree_acc_pot_range", "rk_tree_get_group_costs", "rk_tree_exact",
     "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak",
-    "rk_plummer",
+    "rk_plummer", "rk_tree_clone",
 ]
 
 
@@ -85,7 +85,8 @@ def lib():
     L.rk_tree_set_stream.argtypes = [vp, vp]
     L.rk_tree_synchronize.argtypes = [vp]
     L.rk_tree_build.argtypes = [vp, vp, vp, vp, vp, sz, i32, dbl, i32, sz, sz, C.POINTER(BuildInfo)]
-    L.rk_tree_update_positions.argtypes = [vp, vp, vp, vp, i32, C.POINTER(BuildInfo)]
+    L.rk_tree_update_positions.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(BuildInfo)]
+    L.rk_tree_clone.argtypes = [vp, vp]
     L.rk_tree_update_masses.argtypes = [vp, vp, i32]
     L.rk_tree_clear.argtypes = [vp]
     for f in ("rk_tree_nparts", "rk_tree_nnodes", "rk_tree_ncrit"):
@@ -134,7 +135,9 @@ class Octree:
         self.fp = fp
         self.F = FDT[fp]
         self.L = lib()
-        self.h = self.L.rk_tree_create(fp, 0 if mac == "bh" else 1, device)
+        self.mac = 0 if mac == "bh" else 1
+        self.device = device
+        self.h = self.L.rk_tree_create(fp, self.mac, device)
         if not self.h:
             raise RuntimeError(self.L.rk_create_error().decode())
         self.build_info = BuildInfo()
@@ -176,8 +179,13 @@ class Octree:
                                          max_leaf_n, ncrit, C.byref(self.build_info)))
         return self.build_info
 
-    def update_positions(self, x=None, y=None, z=None, where=RK_HOST):
-        arrs = [self._prep(a, where) for a in (x, y, z)]
+    def clone(self):
+        other = Octree(fp=self.fp, mac="bh" if self.mac == 0 else "bh_geom", device=self.device)
+        other._check(self.L.rk_tree_clone(other.h, self.h))
+        return other
+
+    def update_positions(self, x=None, y=None, z=None, m=None, where=RK_HOST):
+        arrs = [self._prep(a, where) for a in (x, y, z, m)]
         self._check(self.L.rk_tree_update_positions(self.h, *[_ptr(a) for a in arrs], where,
                                                     C.byref(self.build_info)))
         return self.build_info
@@ -289,3 +297,29 @@ def plummer(n_total, first=0, count=None, a=1.0, size=0.0, fp=32, chunk=0, nthre
     if rc:
         raise ValueError("rk_plummer: invalid arguments")
     return out
+
+
+def traverse_external_tree(nodes, parts, codes, Q, mac_value, G=1.0, eps2=0.0, mac="bh", fp=32, first=0, ncrit=128,
+                           offset_output=True):
+    """rk_traverse_external_tree: the literal replacement of the reference's cuda_acc_pot_impl
+    (src/rakau_cuda.cu:348-528). `nodes`: DFS AoS (NODE_DTYPE[fp]); `parts`: x, y, z, m in Morton order.
+    Returns (outputs, EvalInfo dict)."""
+    L = lib()
+    F = FDT[fp]
+    n = parts[0].size
+    nres = {0: 3, 1: 1, 2: 4}[Q]
+    out = [np.zeros(n if offset_output else n - first, dtype=F) for _ in range(nres)]
+    optr = (C.c_void_p * 4)(*([_ptr(a) for a in out] + [None] * (4 - nres)))
+    pa = [np.ascontiguousarray(a, dtype=F) for a in parts]
+    pptr = (C.c_void_p * 4)(*[_ptr(a) for a in pa])
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE[fp])
+    split = np.array([first, n], dtype=np.uint64)
+    codes = np.ascontiguousarray(codes, dtype=np.uint64)
+    info = EvalInfo()
+    err = C.create_string_buffer(512)
+    rc = L.rk_traverse_external_tree(fp, 0 if mac == "bh" else 1, Q, optr, _ptr(split), 2, _ptr(nodes), nodes.size,
+                                     pptr, _ptr(codes), n, float(mac_value), float(G), float(eps2),
+                                     1 if offset_output else 0, ncrit, C.byref(info), err, 512)
+    if rc:
+        raise RakauError(rc, err.value.decode())
+    return out, info.asdict()

@@ -158,20 +158,71 @@ public:
         }
     }
 
+    // ---- copy constructor, tree.hpp:1735-1743: deep device-to-device copy -----------------------------------
+    void clone_from(const tree &o)
+    {
+        use();
+        clear();
+        const size_t n = o.m_b.n, M = o.m_b.n_nodes, C = o.m_b.n_crit;
+        m_box = o.m_box;
+        m_box_deduced = o.m_box_deduced;
+        m_max_leaf_n = o.m_max_leaf_n;
+        m_ncrit = o.m_ncrit;
+        m_max_group = o.m_max_group;
+        m_b.n = n;
+        m_b.n_nodes = M;
+        m_b.n_crit = C;
+        m_b.levels = o.m_b.levels;
+        if (!n) {
+            return;
+        }
+        RK_CUDA_CHECK(cudaStreamSynchronize(o.m_stream));
+        reserve_particles(n);
+        auto cp = [this](void *dst, const void *src, size_t bytes) {
+            if (bytes) {
+                RK_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, m_stream));
+            }
+        };
+        cp(m_b.psorted.p, o.m_b.psorted.p, n * sizeof(vec4<F>));
+        cp(m_b.keys_a.p, o.m_b.codes, n * sizeof(u64));
+        cp(m_b.idx_a.p, o.m_b.last_perm, n * sizeof(u32));
+        m_b.codes = m_b.keys_a.p;
+        m_b.last_perm = m_b.idx_a.p;
+        cp(m_b.perm.p, o.m_b.perm.p, n * sizeof(u32));
+        cp(m_b.inv_perm.p, o.m_b.inv_perm.p, n * sizeof(u32));
+        m_b.nodeA.reserve(M, 1.1);
+        m_b.nodeB.reserve(M, 1.1);
+        m_b.node_dfs.reserve(M, 1.1);
+        m_b.node_ndesc.reserve(M, 1.1);
+        m_b.crit_node.reserve(C, 1.1);
+        m_b.crit_begin.reserve(C + 1, 1.1);
+        cp(m_b.nodeA.p, o.m_b.nodeA.p, M * sizeof(vec4<F>));
+        cp(m_b.nodeB.p, o.m_b.nodeB.p, M * sizeof(uint4));
+        cp(m_b.node_dfs.p, o.m_b.node_dfs.p, M * sizeof(u32));
+        cp(m_b.node_ndesc.p, o.m_b.node_ndesc.p, M * sizeof(u32));
+        if (m_mac == RK_MAC_BH_GEOM) {
+            m_b.node_delta.reserve(M, 1.1);
+            cp(m_b.node_delta.p, o.m_b.node_delta.p, M * sizeof(F));
+        }
+        cp(m_b.crit_node.p, o.m_b.crit_node.p, C * sizeof(u32));
+        cp(m_b.crit_begin.p, o.m_b.crit_begin.p, (C + 1) * sizeof(u32));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+
     // ---- sync(), tree.hpp:3678-3743 ------------------------------------------------------------------------
-    void update_positions(const void *x, const void *y, const void *z, int where, rk_build_info *info)
+    void update_positions(const void *x, const void *y, const void *z, const void *m, int where, rk_build_info *info)
     {
         use();
         const size_t n = m_b.n;
         try {
             RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[0], m_stream));
             const F *dx, *dy, *dz, *dm;
-            upload4(x, y, z, nullptr, n, where, dx, dy, dz, dm);
+            upload4(x, y, z, m, n, where, dx, dy, dz, dm);
             reset_flags();
             // the current Morton order becomes the pre-sort order of the new build
             std::swap(m_b.pin.p, m_b.psorted.p);
             std::swap(m_b.pin.cap, m_b.psorted.cap);
-            launch_set_coords<F>(m_b.pin.p, dx, dy, dz, nullptr, n, reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
+            launch_set_coords<F>(m_b.pin.p, dx, dy, dz, dm, n, reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
             rebuild(false, info);
         } catch (...) {
             clear();
@@ -449,6 +500,183 @@ public:
             RK_CUDA_CHECK(cudaEventElapsedTime(&info->ms_total, m_ev.ev[4], m_ev.ev[7]));
             // interactions = sum over groups of T*(leaf sources + accepted) + T*(T-1)
             info->interactions = info->p2p_pairs + 2 * info->self_pairs + m_hpin[4]; // [4] = sum T * accepted
+        }
+    }
+
+
+    // ---- literal drop-in for cuda_acc_pot_impl (rakau_cuda.cu:348-528): traverse a host-built tree ----------
+    // The DFS AoS node array of the reference is re-laid level-major on the host (O(M) loops), uploaded together
+    // with the particles, and walked by the same kernel as the device-built trees.
+    void traverse_external(int Q, void *const out[4], const uint64_t *split_indices, size_t nsplit,
+                           const host_node_t<F> *nodes, size_t M, const void *const parts[4], size_t n, F mac_value,
+                           F G, F eps2, bool offset_output, size_t ncrit, rk_eval_info *info)
+    {
+        use();
+        clear();
+        if (info) {
+            std::memset(info, 0, sizeof(*info));
+        }
+        if (Q < 0 || Q > 2 || !nsplit || !nodes || !M || !n) {
+            if (!n || !M) {
+                return;
+            }
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_traverse_external_tree: invalid arguments");
+        }
+        if (!ncrit) {
+            ncrit = 128; // the reference's default_ncrit (tree.hpp:589-595)
+        }
+        if (n > 0xfffffff0ull || M > 0xfffffff0ull / 8) {
+            throw api_error(RK_ERR_OVERFLOW, "rk_traverse_external_tree: the tree is too large");
+        }
+        const size_t first = static_cast<size_t>(split_indices[0]);
+        if (first >= n) {
+            return; // everything stays on the caller's CPU share
+        }
+        // level-major order
+        u32 cnt[NLEVELS] = {};
+        for (size_t k = 0; k < M; ++k) {
+            if (nodes[k].level >= u64(NLEVELS)) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_traverse_external_tree: node level out of range");
+            }
+            ++cnt[nodes[k].level];
+        }
+        u32 run[NLEVELS];
+        u32 acc = 0;
+        for (int l = 0; l < NLEVELS; ++l) {
+            m_b.levels.base[l] = acc;
+            run[l] = acc;
+            acc += cnt[l];
+        }
+        m_b.levels.base[NLEVELS] = acc;
+        m_b.levels.base[NLEVELS + 1] = acc;
+        std::vector<u32> bfs(M);
+        for (size_t k = 0; k < M; ++k) {
+            bfs[k] = run[nodes[k].level]++;
+        }
+        std::vector<vec4<F>> hA(M);
+        std::vector<uint4> hB(M);
+        std::vector<F> hD(m_mac == RK_MAC_BH_GEOM ? M : 0);
+        F tab[NLEVELS] = {};
+        for (size_t k = 0; k < M; ++k) {
+            const auto &nd = nodes[k];
+            u32 nch = 0;
+            for (size_t c = k + 1, e = k + nd.n_children; c <= e; c += 1 + nodes[c].n_children) {
+                ++nch;
+            }
+            const u32 b = bfs[k];
+            hA[b] = make_vec4<F>(nd.props[0], nd.props[1], nd.props[2], nd.props[3]);
+            hB[b] = make_uint4(static_cast<u32>(nd.begin), static_cast<u32>(nd.end), nd.n_children ? bfs[k + 1] : 0u,
+                               (static_cast<u32>(nd.level) << 8) | nch);
+            if (m_mac == RK_MAC_BH_GEOM) {
+                hD[b] = nd.delta;
+            }
+            tab[nd.level] = nd.dim; // dim2 (bh) or dim (bh_geom): a function of the level only
+        }
+        // critical nodes: first node on each root path with <= ncrit particles, or a leaf (tree.hpp:801-803)
+        std::vector<u32> hcn, hcb;
+        size_t max_group = 0;
+        for (size_t k = 0; k < M;) {
+            const auto &nd = nodes[k];
+            const size_t np = nd.end - nd.begin;
+            if (np <= ncrit || !nd.n_children) {
+                hcn.push_back(bfs[k]);
+                hcb.push_back(static_cast<u32>(nd.begin));
+                max_group = std::max(max_group, np);
+                k += 1 + nd.n_children;
+            } else {
+                ++k;
+            }
+        }
+        const size_t C = hcn.size();
+        hcb.push_back(static_cast<u32>(n));
+        // first critical node of the GPU share: split_indices[0] was snapped to a node boundary by the caller
+        const size_t c0 = std::lower_bound(hcb.begin(), hcb.begin() + C, static_cast<u32>(first)) - hcb.begin();
+        if (c0 == C || hcb[c0] != first) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_traverse_external_tree: split_indices[0] is not the first "
+                                                     "particle of a critical node for the given ncrit");
+        }
+        // upload
+        m_b.n = n;
+        m_b.n_nodes = M;
+        m_b.n_crit = C;
+        m_max_group = max_group;
+        reserve_particles(n);
+        const F *dx, *dy, *dz, *dm;
+        upload4(parts[0], parts[1], parts[2], parts[3], n, RK_HOST, dx, dy, dz, dm);
+        reset_flags();
+        launch_pack_absmax<F>(dx, dy, dz, dm, m_b.psorted.p, n, reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
+        m_b.nodeA.reserve(M, 1.0);
+        m_b.nodeB.reserve(M, 1.0);
+        m_b.crit_node.reserve(C, 1.0);
+        m_b.crit_begin.reserve(C + 1, 1.0);
+        auto up = [this](void *dst, const void *src, size_t bytes) {
+            RK_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m_stream));
+        };
+        up(m_b.nodeA.p, hA.data(), M * sizeof(vec4<F>));
+        up(m_b.nodeB.p, hB.data(), M * sizeof(uint4));
+        if (m_mac == RK_MAC_BH_GEOM) {
+            m_b.node_delta.reserve(M, 1.0);
+            up(m_b.node_delta.p, hD.data(), M * sizeof(F));
+        }
+        up(m_b.crit_node.p, hcn.data(), C * sizeof(u32));
+        up(m_b.crit_begin.p, hcb.data(), (C + 1) * sizeof(u32));
+
+        trav_params<F> p{};
+        p.parts = m_b.psorted.p;
+        p.nodeA = m_b.nodeA.p;
+        p.nodeB = m_b.nodeB.p;
+        p.node_delta = m_b.node_delta.p;
+        p.crit_node = m_b.crit_node.p;
+        p.crit_begin = m_b.crit_begin.p;
+        p.c0 = static_cast<u32>(c0);
+        p.c1 = static_cast<u32>(C);
+        p.work_counter = m_work.p;
+        for (int l = 0; l < NLEVELS; ++l) {
+            p.mac_tab[l] = (m_mac == RK_MAC_BH) ? tab[l] * mac_value : tab[l];
+        }
+        p.mac_value = mac_value;
+        p.eps2 = eps2;
+        p.G = G;
+        p.perm = nullptr;
+        m_group_cost.reserve(C, 1.0);
+        RK_CUDA_CHECK(cudaMemsetAsync(m_group_cost.p, 0, C * sizeof(u64), m_stream));
+        p.group_cost = m_group_cost.p;
+        p.counters = reinterpret_cast<u64 *>(m_counters.p);
+        const u32 tmax = static_cast<u32>((std::min<size_t>(max_group, 256) + 31) / 32 * 32);
+        p.tmax = tmax ? tmax : 32;
+        p.err = m_work.p + 1;
+        p.out_offset = static_cast<u32>(first);
+        const int nres = Q == 0 ? 3 : (Q == 1 ? 1 : 4);
+        const size_t cnt_out = n - first;
+        for (int j = 0; j < nres; ++j) {
+            m_out[j].reserve(cnt_out, 1.0);
+            p.out[j] = m_out[j].p;
+        }
+        RK_CUDA_CHECK(cudaMemsetAsync(m_work.p, 0, 4 * sizeof(u32), m_stream));
+        RK_CUDA_CHECK(cudaMemsetAsync(m_counters.p, 0, 8 * sizeof(u64), m_stream));
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
+        launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream);
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
+        for (int j = 0; j < nres; ++j) {
+            F *dst = static_cast<F *>(out[j]) + (offset_output ? first : 0);
+            RK_CUDA_CHECK(cudaMemcpyAsync(dst, p.out[j], cnt_out * sizeof(F), cudaMemcpyDeviceToHost, m_stream));
+        }
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 8, m_work.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        if (reinterpret_cast<const u32 *>(m_hpin + 8)[1]) {
+            throw api_error(RK_ERR_RUNTIME, "Traversal stack overflow in the CUDA kernel");
+        }
+        if (info) {
+            info->mac_tests = m_hpin[0];
+            info->accepted = m_hpin[1];
+            info->p2p_pairs = m_hpin[2];
+            info->self_pairs = m_hpin[3];
+            info->interactions = info->p2p_pairs + 2 * info->self_pairs + m_hpin[4];
+            info->n_groups = C - c0;
+            info->kernel_launches = 1;
+            RK_CUDA_CHECK(cudaEventElapsedTime(&info->ms_kernel, m_ev.ev[5], m_ev.ev[6]));
+            info->ms_total = info->ms_kernel;
         }
     }
 
@@ -854,13 +1082,27 @@ int rk_tree_build(rk_tree *t, const void *x, const void *y, const void *z, const
     return guarded(
         t, [&]() { RK_WITH(t, T.build(x, y, z, m, n, where, box_size, deduce_box != 0, max_leaf_n, ncrit, info)); });
 }
-int rk_tree_update_positions(rk_tree *t, const void *x, const void *y, const void *z, int where, rk_build_info *info)
+int rk_tree_update_positions(rk_tree *t, const void *x, const void *y, const void *z, const void *m, int where,
+                             rk_build_info *info)
 {
-    return guarded(t, [&]() { RK_WITH(t, T.update_positions(x, y, z, where, info)); });
+    return guarded(t, [&]() { RK_WITH(t, T.update_positions(x, y, z, m, where, info)); });
 }
 int rk_tree_update_masses(rk_tree *t, const void *m, int where)
 {
     return guarded(t, [&]() { RK_WITH(t, T.update_masses(m, where)); });
+}
+int rk_tree_clone(rk_tree *dst, const rk_tree *src)
+{
+    if (!src || !dst || src->fp != dst->fp || src->mac != dst->mac) {
+        return RK_ERR_INVALID_ARGUMENT;
+    }
+    return guarded(dst, [&]() {
+        if (dst->fp == 32) {
+            dst->t32->clone_from(*src->t32);
+        } else {
+            dst->t64->clone_from(*src->t64);
+        }
+    });
 }
 int rk_tree_clear(rk_tree *t)
 {
@@ -958,15 +1200,38 @@ int rk_measure_fp32_peak(int device, double *tflops, double *ms)
     }
 }
 
-int rk_traverse_external_tree(int, int, int, void *const[4], const uint64_t *, size_t, const void *, size_t,
-                              const void *const[4], const uint64_t *, size_t, double, double, double, int, size_t,
-                              rk_eval_info *, char *errbuf, size_t errbuf_len)
+int rk_traverse_external_tree(int fp_bits, int mac, int Q, void *const out[4], const uint64_t *split_indices,
+                              size_t nsplit, const void *tree, size_t tree_size, const void *const parts[4],
+                              const uint64_t *codes, size_t nparts, double mac_value, double G, double eps2,
+                              int offset_output, size_t ncrit, rk_eval_info *info, char *errbuf, size_t errbuf_len)
 {
-    if (errbuf && errbuf_len) {
-        std::strncpy(errbuf, "rk_traverse_external_tree: not implemented yet", errbuf_len - 1);
-        errbuf[errbuf_len - 1] = 0;
+    (void)codes; // the grouped traversal identifies ancestors by particle ranges, not by Morton codes
+    rk_tree *t = rk_tree_create(fp_bits, mac, 0);
+    auto fail = [&](int rc, const char *msg) {
+        if (errbuf && errbuf_len) {
+            std::strncpy(errbuf, msg, errbuf_len - 1);
+            errbuf[errbuf_len - 1] = 0;
+        }
+        return rc;
+    };
+    if (!t) {
+        return fail(RK_ERR_RUNTIME, rk_create_error());
     }
-    return RK_ERR_RUNTIME;
+    const int rc = guarded(t, [&]() {
+        if (fp_bits == 32) {
+            t->t32->traverse_external(Q, out, split_indices, nsplit, static_cast<const rk::host_node_t<float> *>(tree),
+                                      tree_size, parts, nparts, static_cast<float>(mac_value), static_cast<float>(G),
+                                      static_cast<float>(eps2), offset_output != 0, ncrit, info);
+        } else {
+            t->t64->traverse_external(Q, out, split_indices, nsplit, static_cast<const rk::host_node_t<double> *>(tree),
+                                      tree_size, parts, nparts, mac_value, G, eps2, offset_output != 0, ncrit, info);
+        }
+    });
+    if (rc != RK_OK) {
+        fail(rc, t->err.c_str());
+    }
+    rk_tree_destroy(t);
+    return rc;
 }
 
 } // extern "C"

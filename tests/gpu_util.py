@@ -3,6 +3,7 @@ import numpy as np
 
 def build_pair(oracle_mod, rk, x, y, z, m, fp=32, mac="bh", **kw):
     o = oracle_mod.OracleTree(x, y, z, m, fp=fp, mac=mac, **kw)
+    o._ncrit = kw.get("ncrit", 128)
     g = rk.Octree(fp=fp, mac=mac)
     g.build(x, y, z, m, **kw)
     return o, g

