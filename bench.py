@@ -172,18 +172,11 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
-def split_by_cost(costs_cum, total, world):
-    """Boundaries (critical-node indices) cutting the cumulative cost into `world` nearly equal parts."""
-    import torch
-    targets = torch.arange(1, world, device=costs_cum.device, dtype=costs_cum.dtype) * (total // world)
-    cuts = torch.searchsorted(costs_cum, targets).tolist()
-    return [0] + [int(c) + 1 for c in cuts] + [int(costs_cum.numel())]
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import rakau_b200 as rk
+    from rakau_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,7 +210,7 @@ def run_ours(args):
     out_dev = [torch.zeros(nparts, dtype=torch.float32, device=dev) for _ in range(3)]
     hout = [torch.empty(nparts, dtype=torch.float32).pin_memory() for _ in range(3)]
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
-    state = {"cuts": None, "crit_begin": None, "info": None, "bi": None}
+    state = {"cuts": None, "crit_begin": None, "info": None, "bi": None, "imbalance": None}
 
     def gather_inputs(src):
         if world == 1:
@@ -238,8 +231,7 @@ def run_ours(args):
             # first evaluation: equal particle counts (tree.hpp:3147-3178 projects shares onto particle indices)
             cr = tree.crit()[:, 1].astype(np.int64)
             state["crit_begin"] = np.concatenate([cr, [nparts]])
-            tg = np.arange(1, world, dtype=np.int64) * (nparts // world)
-            state["cuts"] = [0] + np.searchsorted(cr, tg).tolist() + [C]
+            state["cuts"] = sharding.cuts_by_particles(cr, nparts, world)
         return state["cuts"][rank], state["cuts"][rank + 1]
 
     def step(e2e):
@@ -271,11 +263,9 @@ def run_ours(args):
     def refresh_costs():
         if world == 1:
             return
-        C = tree.ncrit_nodes
-        costs = torch.from_numpy(tree.group_costs().astype(np.int64)).to(dev)
-        dist.all_reduce(costs)
-        cum = torch.cumsum(costs, 0)
-        state["cuts"] = split_by_cost(cum, int(cum[-1].item()), world)
+        costs = sharding.allreduce_costs(tree.group_costs(), dist, dev)
+        state["cuts"] = sharding.cuts_by_cost(costs, world)
+        state["imbalance"] = sharding.imbalance(costs, state["cuts"])
 
     def barrier():
         torch.cuda.synchronize()
@@ -352,7 +342,7 @@ def run_ours(args):
                    "max_leaf_n": args.max_leaf_n, "ncrit": args.ncrit, "mac": "bh", "G": 1.0, "eps": 0.0,
                    "parallelism": f"morton_range_shard{world}" if world > 1 else "single_gpu",
                    "l2": "256 MiB buffer written between timed iterations", "interactions_per_step": inter,
-                   "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"]},
+                   "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"], "shard_cost_imbalance": state["imbalance"]},
         "ms_build": b_ms, "ms_traverse_kernel": k_ms,
         "build_phases_ms": {k: bi[k] for k in ("ms_encode", "ms_sort", "ms_permute", "ms_topology", "ms_props")},
         "roofline": {"bound": "fp32", "kernel": "traverse_kernel<float,0,0>", "achieved": achieved,
