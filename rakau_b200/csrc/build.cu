@@ -271,6 +271,80 @@ __global__ void __launch_bounds__(256) window_final_kernel(const i8 *__restrict_
     lvl[i] = static_cast<i8>(w + 1 > CBITS ? CBITS : w + 1);
 }
 
+
+// Fused form of delta_window + window_double x log2(w) + window_final for windows that fit in shared memory:
+// one CTA computes delta, the leaf level and the critical level of WIN_TILE particles from a staged tile of
+// codes (halo of w2 on both sides); the sliding-window maxima are built by doubling in shared memory.
+constexpr int WIN_TILE = 2048;
+constexpr int WIN_MAXW = 2048;
+
+__device__ __forceinline__ void window_levels_smem(const u64 *__restrict__ sc, int w2, int w, size_t i0, size_t n,
+                                                   i8 *__restrict__ A0, i8 *__restrict__ A1, i8 *__restrict__ out)
+{
+    const int len = WIN_TILE + w;
+    for (int q = threadIdx.x; q < len; q += blockDim.x) {
+        const size_t j = i0 + q;
+        A0[q] = (j >= size_t(w) && j < n) ? static_cast<i8>(shared_digits(sc[q + w2 - w], sc[q + w2])) : i8(-1);
+    }
+    __syncthreads();
+    int k = 1;
+    i8 *in = A0, *ot = A1;
+    while (2 * k <= w + 1) {
+        for (int q = threadIdx.x; q < len; q += blockDim.x) {
+            const i8 a = in[q], b = (q + k < len) ? in[q + k] : i8(-1);
+            ot[q] = a > b ? a : b;
+        }
+        __syncthreads();
+        i8 *t = in;
+        in = ot;
+        ot = t;
+        k *= 2;
+    }
+    const int off = w + 1 - k;
+    for (int q = threadIdx.x; q < WIN_TILE; q += blockDim.x) {
+        const size_t i = i0 + q;
+        if (i < n) {
+            const i8 a = in[q], b = in[q + off];
+            const int v = a > b ? a : b;
+            out[i] = static_cast<i8>(v + 1 > CBITS ? CBITS : v + 1);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) window_fused_kernel(const u64 *__restrict__ codes, size_t n, int w1, int w2,
+                                                           i8 *__restrict__ delta, i8 *__restrict__ lvl_leaf,
+                                                           i8 *__restrict__ lvl_crit)
+{
+    extern __shared__ __align__(16) unsigned char win_smem[];
+    u64 *sc = reinterpret_cast<u64 *>(win_smem); // codes of particles i0 - w2 .. i0 + WIN_TILE + w2
+    i8 *A0 = reinterpret_cast<i8 *>(sc + WIN_TILE + 2 * w2);
+    i8 *A1 = A0 + WIN_TILE + w2;
+    const size_t i0 = size_t(blockIdx.x) * WIN_TILE;
+    for (int s = threadIdx.x; s < WIN_TILE + 2 * w2; s += blockDim.x) {
+        const long long j = static_cast<long long>(i0) - w2 + s;
+        sc[s] = (j >= 0 && static_cast<size_t>(j) < n) ? codes[j] : 0ull;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < WIN_TILE; q += blockDim.x) {
+        const size_t i = i0 + q;
+        if (i < n) {
+            delta[i] = i ? static_cast<i8>(shared_digits(sc[q + w2 - 1], sc[q + w2])) : i8(-1);
+        }
+    }
+    window_levels_smem(sc, w2, w1, i0, n, A0, A1, lvl_leaf);
+    if (w2 != w1) {
+        window_levels_smem(sc, w2, w2, i0, n, A0, A1, lvl_crit);
+    } else {
+        for (int q = threadIdx.x; q < WIN_TILE; q += blockDim.x) {
+            const size_t i = i0 + q;
+            if (i < n) {
+                lvl_crit[i] = lvl_leaf[i];
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_i8_kernel(i8 *p, size_t n, i8 v)
 {
     const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
@@ -281,6 +355,8 @@ __global__ void __launch_bounds__(256) fill_i8_kernel(i8 *p, size_t n, i8 v)
 
 // Per tile of TOPO_TILE particles: number of nodes beginning in the tile at each level (rows 0..21) and the
 // number of critical nodes beginning in the tile (row 22). tilecnt is row-major [NLEVELS+1][ntiles].
+// Each warp only visits the levels that occur among its 32 particles (REDUX min/max): in a Plummer sphere the
+// nodes beginning at neighbouring particles span 2-4 levels, not 22.
 __global__ void __launch_bounds__(TOPO_TILE)
     topo_count_kernel(const i8 *__restrict__ delta, const i8 *__restrict__ lvl_leaf, const i8 *__restrict__ lvl_crit,
                       size_t n, u32 ntiles, u32 *__restrict__ tilecnt)
@@ -295,8 +371,8 @@ __global__ void __launch_bounds__(TOPO_TILE)
     const int lo = valid ? delta[i] + 1 : 64, hi = valid ? lvl_leaf[i] : -1;
     const bool critb = valid && (lo <= lvl_crit[i]);
     const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int l = 0; l < NLEVELS; ++l) {
+    const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
+    for (int l = wlo; l <= whi; ++l) {
         const u32 b = __ballot_sync(0xffffffffu, lo <= l && l <= hi);
         if (lane == 0 && b) {
             atomicAdd(&cnt[l], __popc(b));
@@ -315,7 +391,7 @@ __global__ void __launch_bounds__(TOPO_TILE)
 }
 
 // Emits the nodes that begin in this tile (BFS positions from the scanned tile counts) and the critical
-// nodes. nodeB.y (end) and the child count are filled by topo_finalize_kernel.
+// nodes. nodeB.y (end) and the child count are filled by topo_finalize_kernel / topo_children_kernel.
 __global__ void __launch_bounds__(TOPO_TILE)
     topo_emit_kernel(const i8 *__restrict__ delta, const i8 *__restrict__ lvl_leaf, const i8 *__restrict__ lvl_crit,
                      size_t n, u32 ntiles, const u32 *__restrict__ tilecnt /* scanned */, level_table lt,
@@ -323,7 +399,8 @@ __global__ void __launch_bounds__(TOPO_TILE)
                      u32 *__restrict__ crit_node, u32 *__restrict__ crit_begin, u32 n_nodes, u32 n_crit)
 {
     constexpr int NW = TOPO_TILE / 32;
-    __shared__ u32 wc[NLEVELS + 1][NW];
+    __shared__ u32 wc[NLEVELS + 1][NW]; // per level: count of this warp, then BFS base of this warp
+    __shared__ u32 wprefix[NW];         // nodes (all levels) beginning before this warp's first particle
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t i = size_t(blockIdx.x) * TOPO_TILE + threadIdx.x;
     const bool valid = i < n;
@@ -331,8 +408,12 @@ __global__ void __launch_bounds__(TOPO_TILE)
     const int lc = valid ? lvl_crit[i] : -1;
     const bool critb = valid && (lo <= lc);
     const u32 ltm = lanemask_lt();
-#pragma unroll
-    for (int l = 0; l < NLEVELS; ++l) {
+    const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane <= NLEVELS) {
+        wc[lane][w] = 0;
+    }
+    __syncwarp();
+    for (int l = wlo; l <= whi; ++l) {
         const u32 b = __ballot_sync(0xffffffffu, lo <= l && l <= hi);
         if (lane == 0) {
             wc[l][w] = __popc(b);
@@ -345,6 +426,7 @@ __global__ void __launch_bounds__(TOPO_TILE)
         }
     }
     __syncthreads();
+    // per level: exclusive scan over the warps of the tile, offset by the tile's base and the level's base
     if (threadIdx.x < NLEVELS + 1) {
         const int l = threadIdx.x;
         u32 run = tilecnt[size_t(l) * ntiles + blockIdx.x] + (l < NLEVELS ? lt.base[l] : 0u);
@@ -355,12 +437,20 @@ __global__ void __launch_bounds__(TOPO_TILE)
         }
     }
     __syncthreads();
-    // DFS base of particle i = number of nodes beginning at particles < i = sum over levels of the ranks.
-    u32 dfsb = 0;
-#pragma unroll
-    for (int l = 0; l < NLEVELS; ++l) {
+    // DFS base of the warp = sum over levels of (BFS base of the warp at that level - base of the level)
+    {
+        u32 v = (lane < NLEVELS) ? wc[lane][w] - lt.base[lane] : 0u;
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (lane == 0) {
+            wprefix[w] = v;
+        }
+    }
+    __syncwarp();
+    // DFS base of particle i = nodes beginning at particles < i
+    u32 dfsb = wprefix[w];
+    for (int l = wlo; l <= whi; ++l) {
         const u32 b = __ballot_sync(0xffffffffu, lo <= l && l <= hi);
-        dfsb += wc[l][w] - lt.base[l] + __popc(b & ltm);
+        dfsb += __popc(b & ltm);
     }
     if (valid) {
         dfsbase[i] = dfsb;
@@ -373,20 +463,18 @@ __global__ void __launch_bounds__(TOPO_TILE)
         const u32 b = __ballot_sync(0xffffffffu, critb);
         crit_rank = wc[NLEVELS][w] + __popc(b & ltm);
     }
-    // Emit. rank at level l+1 is needed as the first child of the node at level l.
+    // Emit. The rank at level l+1 is the first child of the node at level l.
     u32 prev_rank = 0;
     bool prev_pred = false;
-#pragma unroll
-    for (int l = 0; l <= NLEVELS; ++l) {
+    for (int l = wlo; l <= whi + 1; ++l) {
         bool pred = false;
         u32 r = 0;
-        if (l < NLEVELS) {
+        if (l <= whi) {
             pred = lo <= l && l <= hi;
             const u32 b = __ballot_sync(0xffffffffu, pred);
             r = wc[l][w] + __popc(b & ltm);
         }
         if (prev_pred) {
-            // node (i, l-1): begin, end (later), first child, level
             nodeB[prev_rank] = make_uint4(static_cast<u32>(i), 0u, pred ? r : 0u, static_cast<u32>(l - 1) << 8);
             node_dfs[prev_rank] = dfsb + static_cast<u32>(l - 1 - lo);
             if (critb && lc == l - 1) {
@@ -564,50 +652,56 @@ __device__ __forceinline__ void node_centre_dev(F out[3], u64 first_code, u32 le
     }
 }
 
-// One warp per node. The reduction shape (lane-strided partial sums over head particles, whole chunks and
-// tail particles, then a fixed shuffle tree) depends only on the node's range, never on the mass values,
-// so scaling all masses by a power of two scales every partial exactly (reference test update_masses.cpp:56-68).
-template <typename F>
-__global__ void __launch_bounds__(256)
-    node_props_kernel(const vec4<F> *__restrict__ p, const u64 *__restrict__ codes, const double *__restrict__ chunks,
-                      const uint4 *__restrict__ nodeB, vec4<F> *__restrict__ nodeA, F *__restrict__ node_delta,
-                      u32 n_nodes, int mac, level_dims<F> ld, u64 *__restrict__ err)
+// Node sums with G lanes per node. The reduction shape (lane-strided partial sums over head particles, whole
+// chunks and tail particles, then a fixed shuffle tree) depends only on the node's range, never on the mass
+// values, so scaling all masses by a power of two scales every partial exactly (reference test
+// update_masses.cpp:56-68).
+template <typename F, int G>
+__device__ __forceinline__ dsum4 node_sum(const vec4<F> *__restrict__ p, const double *__restrict__ chunks, u32 b, u32 e,
+                                          int gl, bool active)
 {
-    const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= n_nodes) {
-        return;
-    }
-    const int lane = threadIdx.x & 31;
-    const uint4 nb = nodeB[k];
-    const u32 b = nb.x, e = nb.y, level = nb.w >> 8;
     dsum4 s{0, 0, 0, 0};
-    const u32 cb = (b + PROPS_CHUNK - 1) / PROPS_CHUNK, ce = e / PROPS_CHUNK;
-    if (cb >= ce) {
-        for (u32 i = b + lane; i < e; i += 32) {
-            const vec4<F> v = p[i];
-            dsum_add_particle(s, v.x, v.y, v.z, v.w);
-        }
-    } else {
-        for (u32 i = b + lane; i < cb * PROPS_CHUNK; i += 32) {
-            const vec4<F> v = p[i];
-            dsum_add_particle(s, v.x, v.y, v.z, v.w);
-        }
-        for (u32 c = cb + lane; c < ce; c += 32) {
-            const double4 cs = *reinterpret_cast<const double4 *>(chunks + size_t(c) * 4);
-            s.m += cs.x;
-            s.x += cs.y;
-            s.y += cs.z;
-            s.z += cs.w;
-        }
-        for (u32 i = ce * PROPS_CHUNK + lane; i < e; i += 32) {
-            const vec4<F> v = p[i];
-            dsum_add_particle(s, v.x, v.y, v.z, v.w);
+    if (active) {
+        const u32 cb = (b + PROPS_CHUNK - 1) / PROPS_CHUNK, ce = e / PROPS_CHUNK;
+        if (cb >= ce) {
+            for (u32 i = b + gl; i < e; i += G) {
+                const vec4<F> v = p[i];
+                dsum_add_particle(s, v.x, v.y, v.z, v.w);
+            }
+        } else {
+            for (u32 i = b + gl; i < cb * PROPS_CHUNK; i += G) {
+                const vec4<F> v = p[i];
+                dsum_add_particle(s, v.x, v.y, v.z, v.w);
+            }
+            for (u32 c = cb + gl; c < ce; c += G) {
+                const double4 cs = *reinterpret_cast<const double4 *>(chunks + size_t(c) * 4);
+                s.m += cs.x;
+                s.x += cs.y;
+                s.y += cs.z;
+                s.z += cs.w;
+            }
+            for (u32 i = ce * PROPS_CHUNK + gl; i < e; i += G) {
+                const vec4<F> v = p[i];
+                dsum_add_particle(s, v.x, v.y, v.z, v.w);
+            }
         }
     }
-    dsum_warp_reduce(s);
-    if (lane != 0) {
-        return;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        s.m += __shfl_xor_sync(0xffffffffu, s.m, o);
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
     }
+    return s;
+}
+
+// Mass, centre of mass (geometric centre for a massless node, tree.hpp:1176-1185), delta for bh_geom.
+template <typename F>
+__device__ __forceinline__ void node_finalize(const dsum4 &s, u32 k, u32 b, u32 level, const u64 *__restrict__ codes,
+                                              vec4<F> *__restrict__ nodeA, F *__restrict__ node_delta, int mac,
+                                              const level_dims<F> &ld, u64 *__restrict__ err)
+{
     const F tot = static_cast<F>(s.m);
     F com[3], geo[3] = {F(0), F(0), F(0)};
     const u64 c0 = codes[b];
@@ -648,6 +742,57 @@ __global__ void __launch_bounds__(256)
     }
     if (ecode) {
         atomicMin(err, (static_cast<u64>(k) << 8) | ecode);
+    }
+}
+
+constexpr u32 PROPS_SMALL = 64; // nodes up to this size are reduced by 8 lanes, larger ones by a full warp
+
+// 8 lanes per node (86 % of the nodes are leaves with <= 16 particles); larger nodes are queued for the
+// warp-per-node kernel.
+template <typename F>
+__global__ void __launch_bounds__(256)
+    node_props_small_kernel(const vec4<F> *__restrict__ p, const u64 *__restrict__ codes,
+                            const double *__restrict__ chunks, const uint4 *__restrict__ nodeB,
+                            vec4<F> *__restrict__ nodeA, F *__restrict__ node_delta, u32 n_nodes, int mac,
+                            level_dims<F> ld, u64 *__restrict__ err, u32 *__restrict__ big_list,
+                            u32 *__restrict__ big_count)
+{
+    const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int gl = threadIdx.x & 7;
+    const bool in_range = k < n_nodes;
+    uint4 nb = make_uint4(0, 0, 0, 0);
+    if (in_range) {
+        nb = nodeB[k];
+    }
+    const bool small = in_range && (nb.y - nb.x) <= PROPS_SMALL;
+    const dsum4 s = node_sum<F, 8>(p, chunks, nb.x, nb.y, gl, small);
+    if (gl == 0 && in_range) {
+        if (small) {
+            node_finalize<F>(s, k, nb.x, nb.w >> 8, codes, nodeA, node_delta, mac, ld, err);
+        } else {
+            big_list[atomicAdd(big_count, 1u)] = k;
+        }
+    }
+}
+
+// One warp per queued node, persistent grid.
+template <typename F>
+__global__ void __launch_bounds__(256)
+    node_props_big_kernel(const vec4<F> *__restrict__ p, const u64 *__restrict__ codes, const double *__restrict__ chunks,
+                          const uint4 *__restrict__ nodeB, vec4<F> *__restrict__ nodeA, F *__restrict__ node_delta,
+                          int mac, level_dims<F> ld, u64 *__restrict__ err, const u32 *__restrict__ big_list,
+                          const u32 *__restrict__ big_count)
+{
+    const u32 nbig = *big_count;
+    const int lane = threadIdx.x & 31;
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nbig; q += nwarps) {
+        const u32 k = big_list[q];
+        const uint4 nb = nodeB[k];
+        const dsum4 s = node_sum<F, 32>(p, chunks, nb.x, nb.y, lane, true);
+        if (lane == 0) {
+            node_finalize<F>(s, k, nb.x, nb.w >> 8, codes, nodeA, node_delta, mac, ld, err);
+        }
     }
 }
 
@@ -814,13 +959,24 @@ void topology_count(build_arrays<F> &b, size_t max_leaf_n, size_t ncrit, cudaStr
     b.tilecnt.reserve(size_t(NLEVELS + 1) * ntiles, 1.25);
     b.rowtot.reserve(NLEVELS + 1);
     const size_t w1 = max_leaf_n, w2 = ncrit > max_leaf_n ? ncrit : max_leaf_n;
-    i8 *p1 = b.win_a.p, *p2 = (w2 != w1) ? b.win_a.p + n : nullptr;
-    delta_window_kernel<<<div_up(n, 256), 256, 0, st>>>(b.codes, n, w1, w2, b.delta.p, p1, p2); count_launch();
-    window_levels(p1, b.win_b.p, b.lvl_leaf.p, n, w1, st);
-    if (p2) {
-        window_levels(p2, b.win_b.p, b.lvl_crit.p, n, w2, st);
+    if (w2 <= size_t(WIN_MAXW) && w2 >= 1 && w1 < n) {
+        // common case: everything in one shared-memory tiled kernel
+        const size_t smem = size_t(WIN_TILE + 2 * w2) * 8 + 2 * size_t(WIN_TILE + w2);
+        RK_CUDA_CHECK(cudaFuncSetAttribute(window_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+        // windows wider than the particle count give level 0 everywhere: clamp (same result, bounded halo)
+        const int cw2 = static_cast<int>(w2 < n ? w2 : n), cw1 = static_cast<int>(w1);
+        window_fused_kernel<<<div_up(n, WIN_TILE), 256, smem, st>>>(b.codes, n, cw1, cw2 < cw1 ? cw1 : cw2, b.delta.p,
+                                                                  b.lvl_leaf.p, b.lvl_crit.p); count_launch();
     } else {
-        RK_CUDA_CHECK(cudaMemcpyAsync(b.lvl_crit.p, b.lvl_leaf.p, n, cudaMemcpyDeviceToDevice, st));
+        i8 *p1 = b.win_a.p, *p2 = (w2 != w1) ? b.win_a.p + n : nullptr;
+        delta_window_kernel<<<div_up(n, 256), 256, 0, st>>>(b.codes, n, w1, w2, b.delta.p, p1, p2); count_launch();
+        window_levels(p1, b.win_b.p, b.lvl_leaf.p, n, w1, st);
+        if (p2) {
+            window_levels(p2, b.win_b.p, b.lvl_crit.p, n, w2, st);
+        } else {
+            RK_CUDA_CHECK(cudaMemcpyAsync(b.lvl_crit.p, b.lvl_leaf.p, n, cudaMemcpyDeviceToDevice, st));
+        }
     }
     topo_count_kernel<<<ntiles, TOPO_TILE, 0, st>>>(b.delta.p, b.lvl_leaf.p, b.lvl_crit.p, n, ntiles, b.tilecnt.p); count_launch();
     row_scan_kernel<<<NLEVELS + 1, 256, 0, st>>>(b.tilecnt.p, ntiles, b.rowtot.p); count_launch();
@@ -855,9 +1011,17 @@ void node_properties(build_arrays<F> &b, int mac, F box_size, cudaStream_t st)
     const u32 nchunks = div_up(n, PROPS_CHUNK);
     b.chunksum.reserve(size_t(nchunks) * 4, 1.05);
     chunk_sums_kernel<F><<<div_up(size_t(nchunks) * 32, 256), 256, 0, st>>>(b.psorted.p, n, nchunks, b.chunksum.p); count_launch();
-    node_props_kernel<F><<<div_up(size_t(M) * 32, 256), 256, 0, st>>>(
-        b.psorted.p, b.codes, b.chunksum.p, b.nodeB.p, b.nodeA.p, b.node_delta.p, M, mac, make_level_dims<F>(box_size),
-        reinterpret_cast<u64 *>(b.d_err.p) + 1); count_launch();
+    // big-node queue lives in the (now free) window scratch: M u32 entries + the counter in d_misc[3]
+    b.win_b.reserve(size_t(M) * 4 + 16, 1.05);
+    u32 *big_list = reinterpret_cast<u32 *>(b.win_b.p);
+    u32 *big_count = b.d_misc.p + 3;
+    RK_CUDA_CHECK(cudaMemsetAsync(big_count, 0, sizeof(u32), st));
+    const level_dims<F> ld = make_level_dims<F>(box_size);
+    u64 *err = reinterpret_cast<u64 *>(b.d_err.p) + 1;
+    node_props_small_kernel<F><<<div_up(size_t(M) * 8, 256), 256, 0, st>>>(
+        b.psorted.p, b.codes, b.chunksum.p, b.nodeB.p, b.nodeA.p, b.node_delta.p, M, mac, ld, err, big_list, big_count); count_launch();
+    node_props_big_kernel<F><<<148 * 4, 256, 0, st>>>(b.psorted.p, b.codes, b.chunksum.p, b.nodeB.p, b.nodeA.p,
+                                                     b.node_delta.p, mac, ld, err, big_list, big_count); count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }
 
