@@ -231,3 +231,143 @@ class Rng:
         out = np.empty(4 * n, dtype=FDT[fp])
         lib().orc_uniform(fp, n, float(size), self.r, _p(out))
         return out[:n], out[n:2 * n], out[2 * n:3 * n], out[3 * n:]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref: the UNMODIFIED reference header compiled against dependency stand-ins (oracle/ref_shim)
+# ---------------------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def ref_available(variant="scalar"):
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libref_{variant}.so"))
+
+
+def best_ref_variant():
+    """Fastest variant the host CPU can run: avx512 > avx2 (both: reference SIMD path); None if not built."""
+    flags = ""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        pass
+    if "avx512f" in flags and "avx512dq" in flags and ref_available("avx512"):
+        return "avx512"
+    if "avx2" in flags and ref_available("avx2"):
+        return "avx2"
+    return None
+
+
+def ref_lib(variant="scalar"):
+    if variant in _REF:
+        return _REF[variant]
+    L = C.CDLL(os.path.join(_HERE, "_ref", f"libref_{variant}.so"))
+    vp, sz, dbl, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_int
+    L.ref_variant.restype = C.c_char_p
+    L.ref_set_threads.argtypes = [i32]
+    L.ref_create.restype = vp
+    L.ref_create.argtypes = [i32, i32, vp, vp, vp, vp, sz, dbl, i32, sz, sz, C.c_char_p, sz]
+    L.ref_destroy.argtypes = [vp]
+    L.ref_last_error.restype = C.c_char_p
+    L.ref_last_error.argtypes = [vp]
+    for f in ("ref_nparts", "ref_nnodes"):
+        getattr(L, f).restype = sz
+        getattr(L, f).argtypes = [vp]
+    L.ref_box_size.restype = dbl
+    L.ref_box_size.argtypes = [vp]
+    L.ref_get_codes.argtypes = [vp, vp]
+    L.ref_get_perm.argtypes = [vp, i32, vp]
+    L.ref_get_parts.argtypes = [vp, vp, vp, vp, vp]
+    L.ref_get_nodes.argtypes = [vp, vp]
+    L.ref_acc_pot.restype = i32
+    L.ref_acc_pot.argtypes = [vp, i32, dbl, dbl, dbl, vp, vp, vp, vp]
+    L.ref_exact.restype = i32
+    L.ref_exact.argtypes = [vp, sz, dbl, dbl, vp]
+    L.ref_update_positions.restype = i32
+    L.ref_update_positions.argtypes = [vp, vp, vp, vp]
+    L.ref_update_masses.restype = i32
+    L.ref_update_masses.argtypes = [vp, vp]
+    _REF[variant] = L
+    return L
+
+
+class RefTree:
+    """rakau::octree<F, MAC> of the unmodified reference header (shimmed dependencies)."""
+
+    def __init__(self, x, y, z, m, box_size=0.0, max_leaf_n=16, ncrit=128, mac="bh", fp=32, variant="scalar",
+                 nthreads=None):
+        self.fp, self.F = fp, FDT[fp]
+        self.L = ref_lib(variant)
+        self.L.ref_set_threads(nthreads or os.cpu_count() or 1)
+        arrs = [np.ascontiguousarray(a, dtype=self.F) for a in (x, y, z, m)]
+        err = C.create_string_buffer(1024)
+        deduce = 1 if not box_size else 0
+        self.h = self.L.ref_create(fp, 0 if mac == "bh" else 1, *[_p(a) for a in arrs], arrs[0].size,
+                                   float(box_size or 0.0), deduce, max_leaf_n, ncrit, err, 1024)
+        if not self.h:
+            raise OracleError(1, err.value.decode())
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ref_destroy(self.h)
+        except Exception:
+            pass
+
+    def variant(self):
+        return self.L.ref_variant().decode()
+
+    @property
+    def nparts(self):
+        return self.L.ref_nparts(self.h)
+
+    @property
+    def box_size(self):
+        return self.L.ref_box_size(self.h)
+
+    def codes(self):
+        out = np.empty(self.nparts, dtype=np.uint64)
+        self.L.ref_get_codes(self.h, _p(out))
+        return out
+
+    def perm(self, which=0):
+        out = np.empty(self.nparts, dtype=np.uint64)
+        self.L.ref_get_perm(self.h, which, _p(out))
+        return out
+
+    def parts(self):
+        out = [np.empty(self.nparts, dtype=self.F) for _ in range(4)]
+        self.L.ref_get_parts(self.h, *[_p(a) for a in out])
+        return out
+
+    def nodes(self):
+        out = np.empty(self.L.ref_nnodes(self.h), dtype=NODE_DTYPE[self.fp])
+        self.L.ref_get_nodes(self.h, _p(out))
+        return out
+
+    def acc_pot(self, Q, theta, G=1.0, eps=0.0):
+        nres = {0: 3, 1: 1, 2: 4}[Q]
+        out = [np.zeros(self.nparts, dtype=self.F) for _ in range(nres)]
+        ptrs = [_p(a) for a in out] + [None] * (4 - nres)
+        rc = self.L.ref_acc_pot(self.h, Q, float(theta), float(G), float(eps), *ptrs)
+        if rc:
+            raise OracleError(rc, self.L.ref_last_error(self.h).decode())
+        return out
+
+    def exact(self, idx, G=1.0, eps=0.0):
+        out = np.zeros(4, dtype=np.float64)
+        rc = self.L.ref_exact(self.h, idx, float(G), float(eps), _p(out))
+        if rc:
+            raise OracleError(rc, self.L.ref_last_error(self.h).decode())
+        return out
+
+    def update_positions(self, x=None, y=None, z=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=self.F) for a in (x, y, z)]
+        rc = self.L.ref_update_positions(self.h, *[_p(a) for a in arrs])
+        if rc:
+            raise OracleError(rc, self.L.ref_last_error(self.h).decode())
+
+    def update_masses(self, m):
+        m = np.ascontiguousarray(m, dtype=self.F)
+        rc = self.L.ref_update_masses(self.h, _p(m))
+        if rc:
+            raise OracleError(rc, self.L.ref_last_error(self.h).decode())

@@ -17,8 +17,9 @@
 //
 // Parity pin: tests/test_oracle_golden.py checks this file against the known-answer
 // vectors of the reference's own tests (test/node_centre.cpp, test/basic.cpp,
-// test/auto_box_size.cpp, test/morton.cpp, ...) and, when oracle/_ref was built,
-// against the unmodified reference header itself (tests/test_oracle_vs_ref.py).
+// test/auto_box_size.cpp, test/morton.cpp, ...); tests/test_oracle_vs_ref.py checks
+// it BIT FOR BIT against oracle/_ref/libref_scalar.so, the unmodified reference
+// header compiled with -DRAKAU_DISABLE_SIMD against the stand-ins in oracle/ref_shim.
 //
 // The oracle additionally carries the counters the reference lacks: per target
 // group #MAC tests, #accepted nodes, #leaf P2P pairs, #self pairs.

@@ -1,0 +1,2 @@
+// stand-in, see shim_core.hpp
+#include "shim_core.hpp"
