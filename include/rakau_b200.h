@@ -128,6 +128,12 @@ RK_API size_t rk_tree_ncrit(const rk_tree *t);
 RK_API double rk_tree_box_size(const rk_tree *t);
 /* p_its_u(): Morton-ordered SoA (any pointer may be NULL). */
 RK_API int rk_tree_get_parts(rk_tree *t, void *x, void *y, void *z, void *m);
+/* Same, written to DEVICE pointers (device-resident integrators: the leapfrog of benchmark_leapfrog.cpp
+ * without a host round trip). */
+RK_API int rk_tree_get_parts_device(rk_tree *t, void *x, void *y, void *z, void *m);
+/* perm / last_perm / inv_perm as uint32_t[nparts] on the DEVICE (re-indexing velocities after an update,
+ * benchmark_leapfrog.cpp:375-383). */
+RK_API int rk_tree_get_perm_device(rk_tree *t, int which, uint32_t *out);
 /* c_it_u(): sorted Morton codes. */
 RK_API int rk_tree_get_codes(rk_tree *t, uint64_t *codes);
 /* perm()/last_perm()/inv_perm(), widened to 64 bit. */
@@ -173,6 +179,11 @@ RK_API int rk_traverse_external_tree(int fp_bits, int mac, int Q, void *const ou
  * a multiple of `chunk`, so ranks can generate disjoint shards [first, first + count) of one global stream. */
 RK_API int rk_plummer(int fp_bits, size_t n_total, size_t first, size_t count, double a, double size, int mode,
                       size_t chunk, int nthreads, void *m, void *x, void *y, void *z);
+
+/* Plummer positions and velocities of benchmark/benchmark_leapfrog.cpp:49-102, clipped at 10 core radii as at
+ * 191-215 (G = M = 1). Arrays hold n elements; *kept receives the number of particles that survive the clip. */
+RK_API int rk_plummer_leapfrog(int fp_bits, size_t n, double a, void *x, void *y, void *z, void *vx, void *vy,
+                               void *vz, size_t *kept);
 
 /* ---- measurement helpers (bench.py) ------------------------------------------------------------------- */
 /* Kernels launched by this library since it was loaded. */

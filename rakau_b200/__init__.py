@@ -33,7 +33,7 @@ SYMBOLS = [
     "rk_tree_box_size", "rk_tree_get_parts", "rk_tree_get_codes", "rk_tree_get_perm", "rk_tree_get_nodes",
     "rk_tree_get_crit", "rk_tree_acc_pot", "rk_tree_acc_pot_range", "rk_tree_get_group_costs", "rk_tree_exact",
     "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak",
-    "rk_plummer", "rk_tree_clone",
+    "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
 ]
 
 
@@ -111,6 +111,9 @@ def lib():
     L.rk_kernel_launch_count.restype = C.c_ulonglong
     L.rk_measure_fp32_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.rk_plummer.argtypes = [i32, sz, sz, sz, dbl, dbl, i32, sz, i32, vp, vp, vp, vp]
+    L.rk_plummer_leapfrog.argtypes = [i32, sz, dbl, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
+    L.rk_tree_get_parts_device.argtypes = [vp, vp, vp, vp, vp]
+    L.rk_tree_get_perm_device.argtypes = [vp, i32, vp]
     _LIB = L
     return L
 
@@ -214,6 +217,14 @@ class Octree:
         out = [np.empty(self.nparts, dtype=self.F) for _ in range(4)]
         self._check(self.L.rk_tree_get_parts(self.h, *[_ptr(a) for a in out]))
         return out
+
+    def parts_device(self, x, y, z, m):
+        """Morton-ordered SoA into device buffers (torch tensors / device pointers; None = skip)."""
+        self._check(self.L.rk_tree_get_parts_device(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(m)))
+
+    def perm_device(self, out, which=RK_PERM):
+        """perm / last_perm / inv_perm as uint32 into a device buffer of nparts elements."""
+        self._check(self.L.rk_tree_get_perm_device(self.h, which, _ptr(out)))
 
     def codes(self):
         out = np.empty(self.nparts, dtype=np.uint64)
@@ -323,3 +334,14 @@ def traverse_external_tree(nodes, parts, codes, Q, mac_value, G=1.0, eps2=0.0, m
     if rc:
         raise RakauError(rc, err.value.decode())
     return out, info.asdict()
+
+
+def plummer_leapfrog(n, a=1.0, fp=32):
+    """Initial conditions of the reference's benchmark_leapfrog (positions + velocities, clipped at 10a).
+    Returns x, y, z, vx, vy, vz (numpy, length = particles kept)."""
+    out = [np.empty(n, dtype=FDT[fp]) for _ in range(6)]
+    kept = C.c_size_t(0)
+    rc = lib().rk_plummer_leapfrog(fp, n, a, *[_ptr(o) for o in out], C.byref(kept))
+    if rc:
+        raise ValueError("rk_plummer_leapfrog: invalid arguments")
+    return [o[:kept.value] for o in out]

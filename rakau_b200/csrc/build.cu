@@ -630,6 +630,38 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Second level: one warp per super-chunk of PROPS_CHUNK chunks (65536 particles), so that the few huge nodes near
+// the root need O(N / 65536 / 32) iterations instead of O(N / 256 / 32) (9 ms at 128 M particles before).
+__global__ void __launch_bounds__(256) chunk_sums2_kernel(const double *__restrict__ c1, u32 nchunks, u32 nsuper,
+                                                           double *__restrict__ out)
+{
+    const u32 sc = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sc >= nsuper) {
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    dsum4 s{0, 0, 0, 0};
+    const u32 b = sc * PROPS_CHUNK;
+#pragma unroll
+    for (int j = 0; j < PROPS_CHUNK / 32; ++j) {
+        const u32 c = b + u32(j) * 32 + lane;
+        if (c < nchunks) {
+            const double4 cs = *reinterpret_cast<const double4 *>(c1 + size_t(c) * 4);
+            s.m += cs.x;
+            s.x += cs.y;
+            s.y += cs.z;
+            s.z += cs.w;
+        }
+    }
+    dsum_warp_reduce(s);
+    if (lane == 0) {
+        out[size_t(sc) * 4 + 0] = s.m;
+        out[size_t(sc) * 4 + 1] = s.x;
+        out[size_t(sc) * 4 + 2] = s.y;
+        out[size_t(sc) * 4 + 3] = s.z;
+    }
+}
+
 template <typename F>
 struct level_dims {
     F dim[NLEVELS];  // box / 2^level  (get_node_dim, tree.hpp:443-448)
@@ -657,33 +689,40 @@ __device__ __forceinline__ void node_centre_dev(F out[3], u64 first_code, u32 le
 // values, so scaling all masses by a power of two scales every partial exactly (reference test
 // update_masses.cpp:56-68).
 template <typename F, int G>
-__device__ __forceinline__ dsum4 node_sum(const vec4<F> *__restrict__ p, const double *__restrict__ chunks, u32 b, u32 e,
-                                          int gl, bool active)
+__device__ __forceinline__ dsum4 node_sum(const vec4<F> *__restrict__ p, const double *__restrict__ chunks,
+                                          const double *__restrict__ chunks2, u32 b, u32 e, int gl, bool active)
 {
     dsum4 s{0, 0, 0, 0};
+    auto add_particles = [&](u32 i0, u32 i1) {
+        for (u32 i = i0 + gl; i < i1; i += G) {
+            const vec4<F> v = p[i];
+            dsum_add_particle(s, v.x, v.y, v.z, v.w);
+        }
+    };
+    auto add_sums = [&](const double *__restrict__ arr, u32 c0, u32 c1) {
+        for (u32 c = c0 + gl; c < c1; c += G) {
+            const double4 cs = *reinterpret_cast<const double4 *>(arr + size_t(c) * 4);
+            s.m += cs.x;
+            s.x += cs.y;
+            s.y += cs.z;
+            s.z += cs.w;
+        }
+    };
     if (active) {
         const u32 cb = (b + PROPS_CHUNK - 1) / PROPS_CHUNK, ce = e / PROPS_CHUNK;
         if (cb >= ce) {
-            for (u32 i = b + gl; i < e; i += G) {
-                const vec4<F> v = p[i];
-                dsum_add_particle(s, v.x, v.y, v.z, v.w);
-            }
+            add_particles(b, e);
         } else {
-            for (u32 i = b + gl; i < cb * PROPS_CHUNK; i += G) {
-                const vec4<F> v = p[i];
-                dsum_add_particle(s, v.x, v.y, v.z, v.w);
+            add_particles(b, cb * PROPS_CHUNK);
+            const u32 sb = (cb + PROPS_CHUNK - 1) / PROPS_CHUNK, se = ce / PROPS_CHUNK;
+            if (sb >= se) {
+                add_sums(chunks, cb, ce);
+            } else {
+                add_sums(chunks, cb, sb * PROPS_CHUNK);
+                add_sums(chunks2, sb, se);
+                add_sums(chunks, se * PROPS_CHUNK, ce);
             }
-            for (u32 c = cb + gl; c < ce; c += G) {
-                const double4 cs = *reinterpret_cast<const double4 *>(chunks + size_t(c) * 4);
-                s.m += cs.x;
-                s.x += cs.y;
-                s.y += cs.z;
-                s.z += cs.w;
-            }
-            for (u32 i = ce * PROPS_CHUNK + gl; i < e; i += G) {
-                const vec4<F> v = p[i];
-                dsum_add_particle(s, v.x, v.y, v.z, v.w);
-            }
+            add_particles(ce * PROPS_CHUNK, e);
         }
     }
 #pragma unroll
@@ -765,7 +804,7 @@ __global__ void __launch_bounds__(256)
         nb = nodeB[k];
     }
     const bool small = in_range && (nb.y - nb.x) <= PROPS_SMALL;
-    const dsum4 s = node_sum<F, 8>(p, chunks, nb.x, nb.y, gl, small);
+    const dsum4 s = node_sum<F, 8>(p, chunks, nullptr, nb.x, nb.y, gl, small);
     if (gl == 0 && in_range) {
         if (small) {
             node_finalize<F>(s, k, nb.x, nb.w >> 8, codes, nodeA, node_delta, mac, ld, err);
@@ -779,9 +818,9 @@ __global__ void __launch_bounds__(256)
 template <typename F>
 __global__ void __launch_bounds__(256)
     node_props_big_kernel(const vec4<F> *__restrict__ p, const u64 *__restrict__ codes, const double *__restrict__ chunks,
-                          const uint4 *__restrict__ nodeB, vec4<F> *__restrict__ nodeA, F *__restrict__ node_delta,
-                          int mac, level_dims<F> ld, u64 *__restrict__ err, const u32 *__restrict__ big_list,
-                          const u32 *__restrict__ big_count)
+                          const double *__restrict__ chunks2, const uint4 *__restrict__ nodeB,
+                          vec4<F> *__restrict__ nodeA, F *__restrict__ node_delta, int mac, level_dims<F> ld,
+                          u64 *__restrict__ err, const u32 *__restrict__ big_list, const u32 *__restrict__ big_count)
 {
     const u32 nbig = *big_count;
     const int lane = threadIdx.x & 31;
@@ -789,7 +828,7 @@ __global__ void __launch_bounds__(256)
     for (u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nbig; q += nwarps) {
         const u32 k = big_list[q];
         const uint4 nb = nodeB[k];
-        const dsum4 s = node_sum<F, 32>(p, chunks, nb.x, nb.y, lane, true);
+        const dsum4 s = node_sum<F, 32>(p, chunks, chunks2, nb.x, nb.y, lane, true);
         if (lane == 0) {
             node_finalize<F>(s, k, nb.x, nb.w >> 8, codes, nodeA, node_delta, mac, ld, err);
         }
@@ -1009,8 +1048,11 @@ void node_properties(build_arrays<F> &b, int mac, F box_size, cudaStream_t st)
         return;
     }
     const u32 nchunks = div_up(n, PROPS_CHUNK);
-    b.chunksum.reserve(size_t(nchunks) * 4, 1.05);
+    const u32 nsuper = div_up(nchunks, PROPS_CHUNK);
+    b.chunksum.reserve((size_t(nchunks) + nsuper) * 4, 1.05);
+    double *chunks2 = b.chunksum.p + size_t(nchunks) * 4;
     chunk_sums_kernel<F><<<div_up(size_t(nchunks) * 32, 256), 256, 0, st>>>(b.psorted.p, n, nchunks, b.chunksum.p); count_launch();
+    chunk_sums2_kernel<<<div_up(size_t(nsuper) * 32, 256), 256, 0, st>>>(b.chunksum.p, nchunks, nsuper, chunks2); count_launch();
     // big-node queue lives in the (now free) window scratch: M u32 entries + the counter in d_misc[3]
     b.win_b.reserve(size_t(M) * 4 + 16, 1.05);
     u32 *big_list = reinterpret_cast<u32 *>(b.win_b.p);
@@ -1020,7 +1062,7 @@ void node_properties(build_arrays<F> &b, int mac, F box_size, cudaStream_t st)
     u64 *err = reinterpret_cast<u64 *>(b.d_err.p) + 1;
     node_props_small_kernel<F><<<div_up(size_t(M) * 8, 256), 256, 0, st>>>(
         b.psorted.p, b.codes, b.chunksum.p, b.nodeB.p, b.nodeA.p, b.node_delta.p, M, mac, ld, err, big_list, big_count); count_launch();
-    node_props_big_kernel<F><<<148 * 4, 256, 0, st>>>(b.psorted.p, b.codes, b.chunksum.p, b.nodeB.p, b.nodeA.p,
+    node_props_big_kernel<F><<<148 * 4, 256, 0, st>>>(b.psorted.p, b.codes, b.chunksum.p, chunks2, b.nodeB.p, b.nodeA.p,
                                                      b.node_delta.p, mac, ld, err, big_list, big_count); count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }

@@ -273,6 +273,21 @@ public:
         }
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
     }
+    void get_parts_device(void *x, void *y, void *z, void *m)
+    {
+        use();
+        launch_unpack<F>(m_b.psorted.p, static_cast<F *>(x), static_cast<F *>(y), static_cast<F *>(z), static_cast<F *>(m),
+                         m_b.n, m_stream);
+        RK_CUDA_CHECK(cudaGetLastError());
+    }
+    void get_perm_device(int which, uint32_t *out)
+    {
+        use();
+        const u32 *src = which == RK_PERM ? m_b.perm.p : (which == RK_LAST_PERM ? m_b.last_perm : m_b.inv_perm.p);
+        if (m_b.n) {
+            RK_CUDA_CHECK(cudaMemcpyAsync(out, src, m_b.n * sizeof(u32), cudaMemcpyDeviceToDevice, m_stream));
+        }
+    }
     void get_codes(uint64_t *codes)
     {
         use();
@@ -1128,6 +1143,14 @@ double rk_tree_box_size(const rk_tree *t)
 int rk_tree_get_parts(rk_tree *t, void *x, void *y, void *z, void *m)
 {
     return guarded(t, [&]() { RK_WITH(t, T.get_parts(x, y, z, m)); });
+}
+int rk_tree_get_parts_device(rk_tree *t, void *x, void *y, void *z, void *m)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_parts_device(x, y, z, m)); });
+}
+int rk_tree_get_perm_device(rk_tree *t, int which, uint32_t *out)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_perm_device(which, out)); });
 }
 int rk_tree_get_codes(rk_tree *t, uint64_t *codes)
 {

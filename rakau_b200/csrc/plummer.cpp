@@ -99,6 +99,63 @@ void gen_chunked(size_t n_total, size_t first, size_t count, F a, F size, size_t
 
 } // namespace
 
+// Initial conditions of benchmark/benchmark_leapfrog.cpp:49-102, 191-215: Plummer positions AND velocities
+// (Aarseth-Henon-Wielen rejection sampling), G = M = 1, one default-seeded mt19937 stream, then clipping at
+// 10 core radii. Returns the number of particles kept (the first *kept entries of every array).
+template <typename F>
+static size_t gen_leapfrog(size_t n, F a, F *x, F *y, F *z, F *vx, F *vy, F *vz)
+{
+    const F pi = static_cast<F>(3.141592653589793238462643383279502884L);
+    const F G(1), M(1);
+    std::mt19937 rng;
+    std::uniform_real_distribution<F> dist1, dist2(F(-1), F(1)), dist3(F(0), F(2) * pi), dist4(F(0), F(1) / F(10));
+    auto rej_sample = [&]() {
+        F xx = F(0), yy = F(1) / F(10);
+        while (yy > xx * xx * std::pow(F(1) - xx * xx, F(7) / F(2))) {
+            xx = dist1(rng);
+            yy = dist4(rng);
+        }
+        return xx;
+    };
+    size_t kept = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const F r = a / std::sqrt(std::pow(dist1(rng), -F(2) / F(3)) - F(1)), theta = std::acos(dist2(rng)),
+                phi = dist3(rng);
+        const F px = r * std::sin(theta) * std::cos(phi), py = r * std::sin(theta) * std::sin(phi),
+                pz = r * std::cos(theta);
+        const F q = rej_sample();
+        const F v = q * std::sqrt(F(2) * G * M / a) * std::pow(F(1) + r * r / (a * a), -F(1) / F(4));
+        const F theta_v = std::acos(dist2(rng)), phi_v = dist3(rng);
+        if (px * px + py * py + pz * pz < F(100) * a * a) {
+            x[kept] = px;
+            y[kept] = py;
+            z[kept] = pz;
+            vx[kept] = v * std::sin(theta_v) * std::cos(phi_v);
+            vy[kept] = v * std::sin(theta_v) * std::sin(phi_v);
+            vz[kept] = v * std::cos(theta_v);
+            ++kept;
+        }
+    }
+    return kept;
+}
+
+extern "C" int rk_plummer_leapfrog(int fp_bits, size_t n, double a, void *x, void *y, void *z, void *vx, void *vy,
+                                   void *vz, size_t *kept)
+{
+    if ((fp_bits != 32 && fp_bits != 64) || !std::isfinite(a) || a <= 0 || !kept) {
+        return RK_ERR_INVALID_ARGUMENT;
+    }
+    if (fp_bits == 32) {
+        *kept = gen_leapfrog<float>(n, float(a), static_cast<float *>(x), static_cast<float *>(y),
+                                    static_cast<float *>(z), static_cast<float *>(vx), static_cast<float *>(vy),
+                                    static_cast<float *>(vz));
+    } else {
+        *kept = gen_leapfrog<double>(n, a, static_cast<double *>(x), static_cast<double *>(y), static_cast<double *>(z),
+                                     static_cast<double *>(vx), static_cast<double *>(vy), static_cast<double *>(vz));
+    }
+    return RK_OK;
+}
+
 extern "C" int rk_plummer(int fp_bits, size_t n_total, size_t first, size_t count, double a, double size, int mode,
                           size_t chunk, int nthreads, void *m, void *x, void *y, void *z)
 {
