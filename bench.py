@@ -246,66 +246,44 @@ def run_ours(args):
     # resident copies of the shard (inputs in HBM when the timed region starts)
     dsh = [t.to(dev, non_blocking=True) for t in (hx, hy, hz, hm)]
     counts = [max(0, min(nparts, min(r * per, nparts) + per) - min(r * per, nparts)) for r in range(world)]
-    full = [torch.empty(nparts, dtype=torch.float32, device=dev) for _ in range(4)] if world > 1 else dsh
     out_dev = [torch.zeros(nparts, dtype=torch.float32, device=dev) for _ in range(3)]
     hout = [torch.empty(nparts, dtype=torch.float32).pin_memory() for _ in range(3)]
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
-    state = {"cuts": None, "crit_begin": None, "info": None, "bi": None, "imbalance": None}
+    state = {"info": None, "bi": None, "imbalance": None, "d2h": 0}
 
-    def gather_inputs(src):
-        if world == 1:
-            return src
-        for j in range(4):
-            if len(set(counts)) == 1:
-                dist.all_gather_into_tensor(full[j], src[j])
-            else:
-                offs = np.cumsum([0] + counts)
-                dist.all_gather([full[j][offs[r]:offs[r + 1]] for r in range(world)], src[j])
-        return full
-
-    def my_range():
-        C = tree.ncrit_nodes
-        if world == 1:
-            return 0, C
-        if state["cuts"] is None:
-            # first evaluation: equal particle counts (tree.hpp:3147-3178 projects shares onto particle indices)
-            cr = tree.crit()[:, 1].astype(np.int64)
-            state["crit_begin"] = np.concatenate([cr, [nparts]])
-            state["cuts"] = sharding.cuts_by_particles(cr, nparts, world)
-        return state["cuts"][rank], state["cuts"][rank + 1]
+    sharded = None
+    if world > 1:
+        from rakau_b200.distributed import ShardedTree
+        sharded = ShardedTree(dist, dev, fp=32, mac="bh", max_leaf_n=args.max_leaf_n, ncrit=args.ncrit)
+        tree = sharded.tree
 
     def step(e2e):
-        if e2e:
-            src = [t.to(dev, non_blocking=True) for t in (hx, hy, hz, hm)]
+        src = [t.to(dev, non_blocking=True) for t in (hx, hy, hz, hm)] if e2e else dsh
+        if world == 1:
+            state["bi"] = tree.build(src[0], src[1], src[2], src[3], max_leaf_n=args.max_leaf_n, ncrit=args.ncrit,
+                                     where=rk.RK_DEVICE, n=nparts)
+            tree.acc_pot(0, args.theta, out=out_dev, where=rk.RK_DEVICE)
+            state["info"] = tree.eval_info.asdict()
+            lo, hi = 0, nparts
         else:
-            src = dsh
-        f = gather_inputs(src)
-        state["bi"] = tree.build(f[0], f[1], f[2], f[3], max_leaf_n=args.max_leaf_n, ncrit=args.ncrit,
-                                 where=rk.RK_DEVICE, n=nparts)
-        c0, c1 = my_range()
-        tree.acc_pot(0, args.theta, out=out_dev, where=rk.RK_DEVICE, crit_range=(c0, c1) if world > 1 else None)
-        state["info"] = tree.eval_info.asdict()
-        if world > 1:
-            # output exchange: every rank owns the Morton-order slice of the critical nodes it evaluated and
-            # broadcasts it in place, so that all ranks end with the full result (as a leapfrog step needs)
-            cb = state["crit_begin"]
-            cuts = state["cuts"]
-            for r in range(world):
-                pb, pe = int(cb[cuts[r]]), int(cb[cuts[r + 1]])
-                if pe > pb:
-                    for j in range(3):
-                        dist.broadcast(out_dev[j][pb:pe], src=r)
+            # distributed sample sort + replicated topology, Morton-range sharded traversal, output exchange
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            state["bi"] = sharded.build(src[0], src[1], src[2], src[3], first_index=first)
+            ev[1].record()
+            state["info"] = sharded.acc_pot(0, args.theta, out_dev)
+            ev[2].record()
+            state["phase_events"] = ev
+            lo, hi = int(sharded.cut_particles[rank]), int(sharded.cut_particles[rank + 1])
         if e2e:
             for j in range(3):
-                hout[j].copy_(out_dev[j], non_blocking=True)
+                hout[j][lo:hi].copy_(out_dev[j][lo:hi], non_blocking=True)  # each rank returns the slice it owns
             stream.synchronize()
+        state["d2h"] = 12 * (hi - lo)
 
     def refresh_costs():
-        if world == 1:
-            return
-        costs = sharding.allreduce_costs(tree.group_costs(), dist, dev)
-        state["cuts"] = sharding.cuts_by_cost(costs, world)
-        state["imbalance"] = sharding.imbalance(costs, state["cuts"])
+        if world > 1:
+            state["imbalance"] = sharded.rebalance()
 
     def barrier():
         torch.cuda.synchronize()
@@ -380,7 +358,7 @@ def run_ours(args):
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"plummer_{nparts}_fp32_theta{args.theta}_accs", "nparts": nparts,
                    "max_leaf_n": args.max_leaf_n, "ncrit": args.ncrit, "mac": "bh", "G": 1.0, "eps": 0.0,
-                   "parallelism": f"morton_range_shard{world}" if world > 1 else "single_gpu",
+                   "parallelism": (f"sample_sort_build+morton_range_traversal_x{world}" if world > 1 else "single_gpu"),
                    "l2": "256 MiB buffer written between timed iterations", "interactions_per_step": inter,
                    "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"], "shard_cost_imbalance": state["imbalance"]},
         "ms_build": b_ms, "ms_traverse_kernel": k_ms,
@@ -394,11 +372,19 @@ def run_ours(args):
                            "unit": "GB/s", "frac": build_bytes / (b_ms * 1e-3) / 1e9 / hbm_peak,
                            "peak_source": "measured" if peaks else "fallback"},
         "e2e": {"value": e2e_value, "unit": "Ginteractions/s", "ms_per_step": e2e_tot_ms / args.steps,
-                "h2d_bytes_per_step": 16 * count, "d2h_bytes_per_step": 12 * nparts},
+                "h2d_bytes_per_step": 16 * count, "d2h_bytes_per_step": state["d2h"],
+                "note": "per rank: its input shard in, the output slice it owns out" if world > 1 else "all inputs in, all outputs out"},
         "gpu_launches": int(launches), "clocks": clk,
         "vs_published_ms": {"note": "reference README traversal-only times, other hardware", "v100_ms": 95,
                             "xeon6148x2_ms": 82, "ours_traverse_ms": k_ms},
     }
+    if world > 1:
+        torch.cuda.synchronize()
+        ev = state["phase_events"]
+        line["ms_build"] = ev[0].elapsed_time(ev[1])
+        line["ms_traverse_and_exchange"] = ev[1].elapsed_time(ev[2])
+        line["build_note"] = ("ms_build = distributed sample sort (local sort, all-to-all, bucket sort, all-gather) + "
+                              "replicated topology/properties; build_phases_ms covers the replicated part only")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             r = cpu_reference_run(args, nparts, 4, 1, args.cpu_seconds)

@@ -97,7 +97,9 @@ RK_API void rk_tree_destroy(rk_tree *t);
 RK_API const char *rk_last_error(const rk_tree *t);
 /* Message of the last failed rk_tree_create (no handle exists to ask). */
 RK_API const char *rk_create_error(void);
-/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this tree. */
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this tree. The handle is
+ * taken literally: 0 is the legacy default stream (torch's default stream); (void*)-1 reverts to the tree's own
+ * non-blocking stream. */
 RK_API int rk_tree_set_stream(rk_tree *t, void *cuda_stream);
 RK_API int rk_tree_synchronize(rk_tree *t);
 
@@ -115,6 +117,19 @@ RK_API int rk_tree_update_positions(rk_tree *t, const void *x, const void *y, co
                                     rk_build_info *info);
 /* update_masses_dispatch, tree.hpp:3782-3805: new masses in the current Morton order; topology untouched. */
 RK_API int rk_tree_update_masses(rk_tree *t, const void *m, int where);
+/* ---- multi-GPU building blocks (one process per GPU; no reference counterpart, the reference is single-process) --
+ * Distributed sample sort: every rank sorts its shard with the GLOBAL box (rk_tree_sort_shard; codes == NULL:
+ * encode first), exchanges splitter buckets (NCCL all-to-all, done by the caller), sorts its bucket again with
+ * the received codes, all-gathers the sorted buckets and builds the replicated tree from the globally sorted
+ * arrays (rk_tree_build_presorted: topology + node properties only). All pointers are DEVICE pointers. */
+RK_API int rk_tree_sort_shard(rk_tree *t, const void *x, const void *y, const void *z, const void *m,
+                              const uint64_t *codes, size_t n, double box_size);
+RK_API int rk_tree_get_codes_device(rk_tree *t, uint64_t *out);
+RK_API int rk_tree_build_presorted(rk_tree *t, const void *x, const void *y, const void *z, const void *m,
+                                   const uint64_t *codes, const uint32_t *perm, size_t n, double box_size,
+                                   size_t max_leaf_n, size_t ncrit, rk_build_info *info);
+/* determine_box_size's final arithmetic (tree.hpp:1309-1312) for a global max |coordinate|. */
+RK_API double rk_deduce_box(int fp_bits, double absmax);
 /* Copy constructor / assignment (tree.hpp:1735-1743, 1785-1822): deep device-to-device copy of src into dst
  * (same fp_bits and mac). */
 RK_API int rk_tree_clone(rk_tree *dst, const rk_tree *src);
@@ -153,6 +168,9 @@ RK_API int rk_tree_acc_pot(rk_tree *t, int Q, int ordered, double theta, double 
  * written for the particles those nodes cover, at their global positions in `out`. */
 RK_API int rk_tree_acc_pot_range(rk_tree *t, int Q, int ordered, double theta, double G, double eps, size_t crit_begin,
                                  size_t crit_end, void *const out[4], int where, rk_eval_info *info);
+/* First particle of the critical nodes idx[0..k) (idx = ncrit gives nparts): the particle range a Morton range of
+ * critical nodes covers, without fetching the whole list. */
+RK_API int rk_tree_crit_begin_at(rk_tree *t, const size_t *idx, size_t k, uint64_t *out);
 /* Per-critical-node interaction counts of the last full evaluation (cost weights for sharding). */
 RK_API int rk_tree_get_group_costs(rk_tree *t, uint64_t *costs);
 /* Device pointer to the same per-critical-node costs (uint64_t[ncrit]); NULL before the first evaluation. */

@@ -34,6 +34,7 @@ SYMBOLS = [
     "rk_tree_get_crit", "rk_tree_acc_pot", "rk_tree_acc_pot_range", "rk_tree_get_group_costs", "rk_tree_exact",
     "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak",
     "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
+    "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
 ]
 
 
@@ -114,6 +115,12 @@ def lib():
     L.rk_plummer_leapfrog.argtypes = [i32, sz, dbl, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     L.rk_tree_get_parts_device.argtypes = [vp, vp, vp, vp, vp]
     L.rk_tree_get_perm_device.argtypes = [vp, i32, vp]
+    L.rk_tree_sort_shard.argtypes = [vp, vp, vp, vp, vp, vp, sz, dbl]
+    L.rk_tree_get_codes_device.argtypes = [vp, vp]
+    L.rk_tree_build_presorted.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, dbl, sz, sz, C.POINTER(BuildInfo)]
+    L.rk_tree_crit_begin_at.argtypes = [vp, vp, sz, vp]
+    L.rk_deduce_box.restype = dbl
+    L.rk_deduce_box.argtypes = [i32, dbl]
     _LIB = L
     return L
 
@@ -167,7 +174,8 @@ class Octree:
         return a
 
     def set_stream(self, stream_ptr):
-        self._check(self.L.rk_tree_set_stream(self.h, C.c_void_p(stream_ptr)))
+        """cudaStream_t handle as an integer; 0 = legacy default stream (torch's default); -1 = the tree's own."""
+        self._check(self.L.rk_tree_set_stream(self.h, C.c_void_p(stream_ptr if stream_ptr >= 0 else 2 ** 64 - 1)))
 
     def synchronize(self):
         self._check(self.L.rk_tree_synchronize(self.h))
@@ -226,6 +234,20 @@ class Octree:
         """perm / last_perm / inv_perm as uint32 into a device buffer of nparts elements."""
         self._check(self.L.rk_tree_get_perm_device(self.h, which, _ptr(out)))
 
+    def sort_shard(self, x, y, z, m, n, box_size, codes=None):
+        """Sort a device-resident shard with the global box (multi-GPU sample sort building block)."""
+        self._check(self.L.rk_tree_sort_shard(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(m), _ptr(codes), n,
+                                              float(box_size)))
+
+    def codes_device(self, out):
+        self._check(self.L.rk_tree_get_codes_device(self.h, _ptr(out)))
+
+    def build_presorted(self, x, y, z, m, codes, perm, n, box_size, max_leaf_n=16, ncrit=128):
+        """Tree (topology + node properties) from globally sorted device arrays."""
+        self._check(self.L.rk_tree_build_presorted(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(m), _ptr(codes), _ptr(perm),
+                                                   n, float(box_size), max_leaf_n, ncrit, C.byref(self.build_info)))
+        return self.build_info
+
     def codes(self):
         out = np.empty(self.nparts, dtype=np.uint64)
         self._check(self.L.rk_tree_get_codes(self.h, _ptr(out)))
@@ -244,6 +266,13 @@ class Octree:
     def crit(self):
         out = np.empty((self.ncrit_nodes, 3), dtype=np.uint64)
         self._check(self.L.rk_tree_get_crit(self.h, _ptr(out)))
+        return out
+
+    def crit_begin_at(self, idx):
+        """First particle of the given critical nodes (index ncrit_nodes -> nparts)."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        out = np.empty(idx.size, dtype=np.uint64)
+        self._check(self.L.rk_tree_crit_begin_at(self.h, _ptr(idx), idx.size, _ptr(out)))
         return out
 
     def group_costs_device_ptr(self):
@@ -280,6 +309,11 @@ class Octree:
 
 def device_count():
     return lib().rk_device_count()
+
+
+def deduce_box(absmax, fp=32):
+    """Box size the library deduces for a given max |coordinate| (tree.hpp:1309-1312)."""
+    return lib().rk_deduce_box(fp, float(absmax))
 
 
 def kernel_launch_count():

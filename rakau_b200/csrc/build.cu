@@ -207,7 +207,19 @@ __global__ void __launch_bounds__(256)
     if (i < n) {
         const u32 p = last_perm[i];
         perm[i] = p;
-        inv_perm[p] = static_cast<u32>(i);
+        if (inv_perm) {
+            inv_perm[p] = static_cast<u32>(i);
+        }
+    }
+}
+
+// perm_to_inv_perm, tree.hpp:1248-1262 (run lazily: only exact_*_o and the inv_perm() getter need it; the
+// scattered 4-byte writes cost 3 ms at 128 M particles).
+__global__ void __launch_bounds__(256) perm_invert_kernel(const u32 *__restrict__ perm, u32 *__restrict__ inv_perm, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        inv_perm[perm[i]] = static_cast<u32>(i);
     }
 }
 
@@ -220,7 +232,9 @@ __global__ void __launch_bounds__(256)
     if (i < n) {
         const u32 p = old_perm[last_perm[i]];
         new_perm[i] = p;
-        inv_perm[p] = static_cast<u32>(i);
+        if (inv_perm) {
+            inv_perm[p] = static_cast<u32>(i);
+        }
     }
 }
 
@@ -968,6 +982,12 @@ void launch_gather(const vec4<F> *pin, const u32 *idx, vec4<F> *pout, size_t n, 
 {
     if (n) {
         gather_kernel<F><<<div_up(n, 256), 256, 0, st>>>(pin, idx, pout, n); count_launch();
+    }
+}
+void launch_perm_invert(const u32 *perm, u32 *inv_perm, size_t n, cudaStream_t st)
+{
+    if (n) {
+        perm_invert_kernel<<<div_up(n, 256), 256, 0, st>>>(perm, inv_perm, n); count_launch();
     }
 }
 void launch_perm_first(const u32 *last_perm, u32 *perm, u32 *inv_perm, size_t n, cudaStream_t st)

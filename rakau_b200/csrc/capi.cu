@@ -89,7 +89,12 @@ public:
         }
     }
     void use() const { RK_CUDA_CHECK(cudaSetDevice(m_device)); }
-    void set_stream(void *s) { m_stream = s ? static_cast<cudaStream_t>(s) : m_own_stream; }
+    // Any cudaStream_t is accepted, INCLUDING 0 (the legacy default stream, which is what torch's default stream
+    // is); (void*)-1 reverts to the tree's own non-blocking stream.
+    void set_stream(void *s)
+    {
+        m_stream = (s == reinterpret_cast<void *>(-1)) ? m_own_stream : static_cast<cudaStream_t>(s);
+    }
     void synchronize()
     {
         use();
@@ -189,7 +194,7 @@ public:
         m_b.codes = m_b.keys_a.p;
         m_b.last_perm = m_b.idx_a.p;
         cp(m_b.perm.p, o.m_b.perm.p, n * sizeof(u32));
-        cp(m_b.inv_perm.p, o.m_b.inv_perm.p, n * sizeof(u32));
+        m_have_inv = false;
         m_b.nodeA.reserve(M, 1.1);
         m_b.nodeB.reserve(M, 1.1);
         m_b.node_dfs.reserve(M, 1.1);
@@ -207,6 +212,98 @@ public:
         cp(m_b.crit_node.p, o.m_b.crit_node.p, C * sizeof(u32));
         cp(m_b.crit_begin.p, o.m_b.crit_begin.p, (C + 1) * sizeof(u32));
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+
+
+    // ---- multi-GPU building blocks (one process per GPU) --------------------------------------
+    // Sort a shard: pack, Morton-encode with the GLOBAL box (or take the given codes), stable radix sort, gather.
+    // Afterwards codes / particles / last_perm of the shard are available on the device; no tree is built.
+    void sort_shard(const void *x, const void *y, const void *z, const void *m, const uint64_t *codes_dev, size_t n,
+                    double box_size)
+    {
+        use();
+        clear();
+        const F bs = static_cast<F>(box_size);
+        if (!std::isfinite(bs) || bs <= F(0)) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_sort_shard needs the global box size");
+        }
+        m_box = bs;
+        m_b.n = n;
+        if (!n) {
+            return;
+        }
+        try {
+            reserve_particles(n);
+            reset_flags();
+            launch_pack_absmax<F>(static_cast<const F *>(x), static_cast<const F *>(y), static_cast<const F *>(z),
+                                  static_cast<const F *>(m), m_b.pin.p, n, reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
+            const F inv_box = F(1) / m_box;
+            if (codes_dev) {
+                RK_CUDA_CHECK(cudaMemcpyAsync(m_b.keys_a.p, codes_dev, n * sizeof(u64), cudaMemcpyDeviceToDevice, m_stream));
+            } else {
+                launch_encode<F>(m_b.pin.p, m_b.keys_a.p, n, inv_box, m_b.d_err.p, m_stream);
+            }
+            u64 *codes;
+            u32 *lperm;
+            radix_sort_pairs(m_b.keys_a.p, m_b.keys_b.p, m_b.idx_a.p, m_b.idx_b.p, n, m_sc, m_stream, &codes, &lperm);
+            m_b.codes = codes;
+            m_b.last_perm = lperm;
+            launch_gather<F>(m_b.pin.p, lperm, m_b.psorted.p, n, m_stream);
+            launch_perm_first(lperm, m_b.perm.p, nullptr, n, m_stream);
+            RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_err.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+            if (!codes_dev) {
+                check_encode_error(m_hpin[0], inv_box);
+            }
+        } catch (...) {
+            clear();
+            throw;
+        }
+    }
+    void get_codes_device(uint64_t *out)
+    {
+        use();
+        if (m_b.n) {
+            RK_CUDA_CHECK(cudaMemcpyAsync(out, m_b.codes, m_b.n * sizeof(u64), cudaMemcpyDeviceToDevice, m_stream));
+        }
+    }
+    // Build the tree from globally sorted device arrays (SoA particles, codes, perm = original index of each
+    // sorted particle): topology + node properties only.
+    void build_presorted(const void *x, const void *y, const void *z, const void *m, const uint64_t *codes_dev,
+                         const uint32_t *perm_dev, size_t n, double box_size, size_t max_leaf_n, size_t ncrit,
+                         rk_build_info *info)
+    {
+        use();
+        clear();
+        const F bs = static_cast<F>(box_size);
+        if (!std::isfinite(bs) || bs <= F(0) || !max_leaf_n || !ncrit) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_build_presorted: invalid arguments");
+        }
+        m_box = bs;
+        m_box_deduced = false;
+        m_max_leaf_n = max_leaf_n;
+        m_ncrit = ncrit;
+        m_b.n = n;
+        try {
+            reserve_particles(n);
+            RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[0], m_stream));
+            reset_flags();
+            launch_pack_absmax<F>(static_cast<const F *>(x), static_cast<const F *>(y), static_cast<const F *>(z),
+                                  static_cast<const F *>(m), m_b.psorted.p, n, reinterpret_cast<u64 *>(m_b.d_misc.p),
+                                  m_stream);
+            RK_CUDA_CHECK(cudaMemcpyAsync(m_b.keys_a.p, codes_dev, n * sizeof(u64), cudaMemcpyDeviceToDevice, m_stream));
+            RK_CUDA_CHECK(cudaMemcpyAsync(m_b.perm.p, perm_dev, n * sizeof(u32), cudaMemcpyDeviceToDevice, m_stream));
+            RK_CUDA_CHECK(cudaMemcpyAsync(m_b.idx_a.p, perm_dev, n * sizeof(u32), cudaMemcpyDeviceToDevice, m_stream));
+            m_b.codes = m_b.keys_a.p;
+            m_b.last_perm = m_b.idx_a.p;
+            for (int k = 1; k <= 3; ++k) {
+                RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[k], m_stream));
+            }
+            finish_build(0, info);
+        } catch (...) {
+            clear();
+            throw;
+        }
     }
 
     // ---- sync(), tree.hpp:3678-3743 ------------------------------------------------------------------------
@@ -283,7 +380,7 @@ public:
     void get_perm_device(int which, uint32_t *out)
     {
         use();
-        const u32 *src = which == RK_PERM ? m_b.perm.p : (which == RK_LAST_PERM ? m_b.last_perm : m_b.inv_perm.p);
+        const u32 *src = which == RK_PERM ? m_b.perm.p : (which == RK_LAST_PERM ? m_b.last_perm : inv_perm_dev());
         if (m_b.n) {
             RK_CUDA_CHECK(cudaMemcpyAsync(out, src, m_b.n * sizeof(u32), cudaMemcpyDeviceToDevice, m_stream));
         }
@@ -296,6 +393,15 @@ public:
             RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
         }
     }
+    // inv_perm is materialised on first use
+    const u32 *inv_perm_dev()
+    {
+        if (!m_have_inv && m_b.n) {
+            launch_perm_invert(m_b.perm.p, m_b.inv_perm.p, m_b.n, m_stream);
+            m_have_inv = true;
+        }
+        return m_b.inv_perm.p;
+    }
     void get_perm(int which, uint64_t *out)
     {
         use();
@@ -303,7 +409,7 @@ public:
         if (!n) {
             return;
         }
-        const u32 *src = which == RK_PERM ? m_b.perm.p : (which == RK_LAST_PERM ? m_b.last_perm : m_b.inv_perm.p);
+        const u32 *src = which == RK_PERM ? m_b.perm.p : (which == RK_LAST_PERM ? m_b.last_perm : inv_perm_dev());
         std::vector<u32> tmp(n);
         RK_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), src, n * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
@@ -336,6 +442,18 @@ public:
         launch_export_crit(m_b.codes, m_b.nodeB.p, m_b.crit_node.p, m_b.crit_begin.p, C, tmp.p, m_stream);
         RK_CUDA_CHECK(cudaMemcpyAsync(crit, tmp.p, 3 * C * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+    // First particle of the given critical nodes (index n_crit gives nparts).
+    void crit_begin_at(const size_t *idx, size_t k, uint64_t *out)
+    {
+        use();
+        host_crit_begin();
+        for (size_t i = 0; i < k; ++i) {
+            if (idx[i] > m_b.n_crit) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT, "critical node index out of range");
+            }
+            out[i] = m_h_crit_begin[idx[i]];
+        }
     }
     const void *group_costs_device() const { return m_costs_valid ? m_group_cost.p : nullptr; }
     void get_group_costs(uint64_t *costs)
@@ -718,7 +836,7 @@ public:
         }
         if (ordered) {
             u32 v;
-            RK_CUDA_CHECK(cudaMemcpyAsync(&v, m_b.inv_perm.p + idx, sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaMemcpyAsync(&v, inv_perm_dev() + idx, sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
             RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
             idx = v;
         }
@@ -828,20 +946,39 @@ private:
         // ---- permute ----
         launch_gather<F>(m_b.pin.p, lperm, m_b.psorted.p, n, m_stream);
         if (first) {
-            launch_perm_first(lperm, m_b.perm.p, m_b.inv_perm.p, n, m_stream);
+            launch_perm_first(lperm, m_b.perm.p, nullptr, n, m_stream);
         } else {
-            launch_perm_compose(m_b.perm.p, lperm, m_b.perm_tmp.p, m_b.inv_perm.p, n, m_stream);
+            launch_perm_compose(m_b.perm.p, lperm, m_b.perm_tmp.p, nullptr, n, m_stream);
             std::swap(m_b.perm.p, m_b.perm_tmp.p);
             std::swap(m_b.perm.cap, m_b.perm_tmp.cap);
         }
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[3], m_stream));
+        m_pending_inv_box = inv_box;
+        m_pending_check_encode = true;
+        finish_build(passes, info);
+    }
+
+    // Topology + node properties on sorted codes / particles (events 0..3 already recorded).
+    void finish_build(int passes, rk_build_info *info)
+    {
+        const size_t n = m_b.n;
+        if (info) {
+            std::memset(info, 0, sizeof(*info));
+        }
+        if (!n) {
+            return;
+        }
+        const F inv_box = m_pending_inv_box;
         // ---- topology: count, size, emit ----
         topology_count<F>(m_b, m_max_leaf_n, m_ncrit, m_stream);
         RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_err.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
         RK_CUDA_CHECK(
             cudaMemcpyAsync(m_hpin + 2, m_b.rowtot.p, (NLEVELS + 1) * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
-        check_encode_error(m_hpin[0], inv_box);
+        if (m_pending_check_encode) {
+            m_pending_check_encode = false;
+            check_encode_error(m_hpin[0], inv_box);
+        }
         const u32 *rt = reinterpret_cast<const u32 *>(m_hpin + 2);
         u64 M = 0;
         for (int l = 0; l < NLEVELS; ++l) {
@@ -877,6 +1014,7 @@ private:
         check_props_error(m_hpin[1]);
         m_max_group = reinterpret_cast<const u32 *>(m_hpin + 2)[2];
         m_costs_valid = false;
+        m_have_inv = false;
         m_h_crit_begin.clear();
         if (info) {
             info->box_size = m_box;
@@ -962,7 +1100,8 @@ private:
     dbuf<F> m_out[4];
     dbuf<u64> m_group_cost, m_counters;
     dbuf<u32> m_work;
-    bool m_costs_valid = false;
+    bool m_costs_valid = false, m_have_inv = false, m_pending_check_encode = false;
+    F m_pending_inv_box = F(0);
     u64 *m_hpin = nullptr; // pinned scratch for small read-backs
     std::vector<u32> m_h_crit_begin;
 };
@@ -1106,6 +1245,32 @@ int rk_tree_update_masses(rk_tree *t, const void *m, int where)
 {
     return guarded(t, [&]() { RK_WITH(t, T.update_masses(m, where)); });
 }
+int rk_tree_sort_shard(rk_tree *t, const void *x, const void *y, const void *z, const void *m, const uint64_t *codes,
+                       size_t n, double box_size)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.sort_shard(x, y, z, m, codes, n, box_size)); });
+}
+int rk_tree_get_codes_device(rk_tree *t, uint64_t *out)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.get_codes_device(out)); });
+}
+int rk_tree_build_presorted(rk_tree *t, const void *x, const void *y, const void *z, const void *m,
+                            const uint64_t *codes, const uint32_t *perm, size_t n, double box_size, size_t max_leaf_n,
+                            size_t ncrit, rk_build_info *info)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.build_presorted(x, y, z, m, codes, perm, n, box_size, max_leaf_n, ncrit, info)); });
+}
+double rk_deduce_box(int fp_bits, double absmax)
+{
+    // determine_box_size, tree.hpp:1309-1312: 2 * max|coord| plus a 5 % slack, in the tree's precision
+    if (fp_bits == 32) {
+        float b = static_cast<float>(absmax) * 2.f;
+        b = std::fma(b, 1.f / 20.f, b);
+        return b;
+    }
+    double b = absmax * 2.;
+    return std::fma(b, 1. / 20., b);
+}
 int rk_tree_clone(rk_tree *dst, const rk_tree *src)
 {
     if (!src || !dst || src->fp != dst->fp || src->mac != dst->mac) {
@@ -1167,6 +1332,10 @@ int rk_tree_get_nodes(rk_tree *t, void *nodes)
 int rk_tree_get_crit(rk_tree *t, rk_cnode *crit)
 {
     return guarded(t, [&]() { RK_WITH(t, T.get_crit(crit)); });
+}
+int rk_tree_crit_begin_at(rk_tree *t, const size_t *idx, size_t k, uint64_t *out)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.crit_begin_at(idx, k, out)); });
 }
 int rk_tree_get_group_costs(rk_tree *t, uint64_t *costs)
 {

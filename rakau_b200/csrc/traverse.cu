@@ -37,7 +37,7 @@ namespace
 
 constexpr int TRAV_WARPS = 4;
 constexpr int TRAV_THREADS = TRAV_WARPS * 32;
-constexpr int LCAP = 128;        // source ring capacity (power of two)
+constexpr int LCAP = 64;         // source ring capacity: two 32-entry blocks (batch being filled + scratch)
 constexpr int STACK_CAP = 512;   // (first child, count) entries per warp (<= 32 pushes per step, depth <= 21)
 constexpr u32 FULL = 0xffffffffu;
 
@@ -178,13 +178,13 @@ __device__ __forceinline__ void eval_slots(const vec4<F> *__restrict__ src, u32 
 template <typename F>
 __host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax)
 {
-    // ring + staged targets + accumulators (2 * tmax entries: up to 2*tmax/32 slots per lane) + stack + small queues
-    return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(2 * tmax) * sizeof(vec4<F>)
+    // ring + staged targets + accumulators (1.5 * tmax entries: up to 1.5*tmax/32 slots per lane) + stack + queues
+    return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(tmax + tmax / 2) * sizeof(vec4<F>)
            + size_t(STACK_CAP) * 4 + 32 * 4 /*nodebuf*/ + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
 }
 
 template <typename F, int Q, int MAC>
-__global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_params<F> p)
+__global__ void __launch_bounds__(TRAV_THREADS, 5) traverse_kernel(const trav_params<F> p)
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) traverse_kernel(const trav_pa
     vec4<F> *ring = reinterpret_cast<vec4<F> *>(base);
     vec4<F> *tgt = ring + LCAP;
     vec4<F> *acc = tgt + p.tmax;
-    u32 *stack = reinterpret_cast<u32 *>(acc + 2 * p.tmax);
-    const u32 rr_cap = 2u * p.tmax / 32u; // accumulator slots per lane
+    u32 *stack = reinterpret_cast<u32 *>(acc + p.tmax + p.tmax / 2);
+    const u32 rr_cap = (p.tmax + p.tmax / 2) / 32u; // accumulator slots per lane
     u32 *nodebuf = stack + STACK_CAP;
     u32 *lq_incl = nodebuf + 32;
     u32 *lq_base = lq_incl + 32;
