@@ -283,7 +283,7 @@ def run_ours(args):
 
     def refresh_costs():
         if world > 1:
-            state["imbalance"] = sharded.rebalance()
+            state["imbalance"] = sharded.rebalance(kernel_ms=state["info"]["ms_kernel"])
 
     def barrier():
         torch.cuda.synchronize()
@@ -311,8 +311,7 @@ def run_ours(args):
     # ---- warm-up (also establishes the cost-weighted split for N > 1) ----
     for w in range(max(args.warmup, 3)):
         step(False)
-        if w == 0:
-            refresh_costs()
+        refresh_costs()  # N > 1: cost-weighted cuts from the previous evaluation (converges in 2-3 steps)
     step(True)
     fp32_peak = rk.measure_fp32_peak(local)
 
@@ -383,6 +382,15 @@ def run_ours(args):
         ev = state["phase_events"]
         line["ms_build"] = ev[0].elapsed_time(ev[1])
         line["ms_traverse_and_exchange"] = ev[1].elapsed_time(ev[2])
+        line["build_phases_rank0_ms"] = sharded.phase_ms()
+        if os.environ.get("RK_DEBUG_BARRIER"):
+            allp = [None] * world
+            dist.all_gather_object(allp, sharded.phase_ms())
+            line["build_phases_all_ranks_ms"] = allp
+        km = torch.tensor([state["info"]["ms_kernel"]], dtype=torch.float64, device=dev)
+        kall = [torch.zeros_like(km) for _ in range(world)]
+        dist.all_gather(kall, km)
+        line["ms_traverse_kernel_per_rank"] = [float(k.item()) for k in kall]
         line["build_note"] = ("ms_build = distributed sample sort (local sort, all-to-all, bucket sort, all-gather) + "
                               "replicated topology/properties; build_phases_ms covers the replicated part only")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -29,6 +29,8 @@ class ShardedTree:
         for t in (self.local, self.bucket, self.tree):
             t.set_stream(s)
         self.nsamp = samples_per_rank
+        self._bufs = {}
+        self.debug_barrier = bool(int(__import__('os').environ.get('RK_DEBUG_BARRIER', '0')))
         self.cuts = None
         self.cut_particles = None  # first particle of every rank's range
 
@@ -37,13 +39,15 @@ class ShardedTree:
         """x, y, z, m: this rank's shard (device tensors); first_index: global index of its first particle."""
         torch, dist = self.torch, self.dist
         n_loc = x.numel()
+        self._ev = [('start', self._rec())]
         amax = torch.stack([x.abs().max(), y.abs().max(), z.abs().max()]).max().double().reshape(1)
         dist.all_reduce(amax, op=dist.ReduceOp.MAX)
         box = deduce_box(float(amax.item()), self.fp)
         # 1. local sort of the shard
         self.local.sort_shard(x, y, z, m, n_loc, box)
-        rows = self._rows_from_tree(self.local, n_loc, offset=int(first_index))
-        codes = rows[:, 0:2].contiguous().view(torch.int64).reshape(-1)
+        codes, sx, sy, sz, sm, lp = self._sorted_arrays(self.local, n_loc)
+        gidx = lp + int(first_index)  # original (global) index of each locally sorted particle
+        self._ev.append(('local_sort', self._rec()))
         # 2. splitters from regular samples (codes are < 2^63, so int64 order == unsigned order)
         pos = (torch.arange(self.nsamp, device=self.dev, dtype=torch.int64) * max(n_loc - 1, 0)) // max(self.nsamp - 1, 1)
         samp = codes[pos] if n_loc else torch.full((self.nsamp,), 2 ** 62, dtype=torch.int64, device=self.dev)
@@ -51,7 +55,8 @@ class ShardedTree:
         dist.all_gather_into_tensor(allsamp, samp)
         allsamp, _ = torch.sort(allsamp)
         split = allsamp[torch.arange(1, self.world, device=self.dev) * self.nsamp]
-        # 3. bucket exchange: ONE all-to-all of 28-byte rows (code, x, y, z, m, original index)
+        self._ev.append(('splitters', self._rec()))
+        # 3. bucket exchange (one all-to-all per array; the arrays stay SoA and contiguous)
         bounds = torch.searchsorted(codes, split, right=False)
         bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=self.dev), bounds,
                             torch.tensor([n_loc], dtype=torch.int64, device=self.dev)])
@@ -60,53 +65,101 @@ class ShardedTree:
         dist.all_to_all_single(recv, send)
         send_l, recv_l = send.tolist(), recv.tolist()
         n_b = int(sum(recv_l))
-        brows = torch.empty((n_b, 7), dtype=torch.int32, device=self.dev)
-        dist.all_to_all_single(brows, rows, output_split_sizes=recv_l, input_split_sizes=send_l)
+
+        def a2a(t):
+            out = torch.empty(n_b, dtype=t.dtype, device=self.dev)
+            dist.all_to_all_single(out, t, output_split_sizes=recv_l, input_split_sizes=send_l)
+            return out
+        bc, bx, by, bz, bm, bi = (a2a(t) for t in (codes, sx, sy, sz, sm, gidx))
+        self._ev.append(('all_to_all', self._rec()))
         # 4. sort the bucket (runs arrive in rank order => stable order of the single-GPU path)
-        bc, bx, by, bz, bm, bi = self._cols(brows)
         self.bucket.sort_shard(bx, by, bz, bm, n_b, box, codes=bc)
-        srows = self._rows_from_tree(self.bucket, n_b, gidx=bi)
-        # 5. ONE all-gather of the sorted buckets, padded to the largest bucket
+        bc, bx, by, bz, bm, blp = self._sorted_arrays(self.bucket, n_b)
+        bi = bi[blp.long()]
+        self._ev.append(('bucket_sort', self._rec()))
+        if self.debug_barrier:
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            self._ev.append(('skew_before_gather', self._rec()))
+        # 5. uneven all-gather of the sorted buckets straight into the full arrays (grouped NCCL send/recv)
         sizes = torch.empty(self.world, dtype=torch.int64, device=self.dev)
         dist.all_gather_into_tensor(sizes, torch.tensor([n_b], dtype=torch.int64, device=self.dev))
-        sizes_l = sizes.tolist()
-        n, mx = int(sum(sizes_l)), int(max(sizes_l))
-        if n_b < mx:
-            srows = torch.cat([srows, torch.zeros((mx - n_b, 7), dtype=torch.int32, device=self.dev)])
-        allrows = torch.empty((self.world, mx, 7), dtype=torch.int32, device=self.dev)
-        dist.all_gather_into_tensor(allrows, srows)
-        full = torch.cat([allrows[r, :sizes_l[r]] for r in range(self.world)]) if min(sizes_l) < mx \
-            else allrows.reshape(-1, 7)
-        fc, fx, fy, fz, fm, fi = self._cols(full)
+        offs = np.concatenate([[0], np.cumsum(sizes.tolist())]).astype(np.int64)
+        n = int(offs[-1])
+        # padded all_gather_into_tensor (NCCL's tuned all-gather: ~600 GB/s per rank on this NVSwitch box, the
+        # grouped send/recv form measured 2x slower here) + one compaction pass
+        sizes_l = [int(offs[r + 1] - offs[r]) for r in range(self.world)]
+        mx = max(sizes_l)
+
+        def gather(key, t):
+            pad = self._persistent('p' + key, mx, t.dtype)
+            pad[:n_b] = t
+            allb = self._persistent('a' + key, mx * self.world, t.dtype)
+            dist.all_gather_into_tensor(allb, pad)
+            if min(sizes_l) == mx:
+                return allb
+            full = self._persistent('f' + key, n, t.dtype)
+            for r in range(self.world):
+                full[int(offs[r]):int(offs[r + 1])] = allb[r * mx:r * mx + sizes_l[r]]
+            return full
+        fc, fx, fy, fz, fm, fi = (gather(k, t) for k, t in zip('cxyzmi', (bc, bx, by, bz, bm, bi)))
+        self._ev.append(('all_gather', self._rec()))
         # 6. replicated topology + node properties
         self.n = n
         self.full_sorted = (fx, fy, fz, fm)  # keep alive
         bi_ = self.tree.build_presorted(fx, fy, fz, fm, fc, fi, n, box, self.mln, self.ncrit)
+        self._ev.append(('topology_props', self._rec()))
         self.cut_particles = None
         return bi_
 
-    def _rows_from_tree(self, t, n, offset=0, gidx=None):
-        """[n, 7] int32 rows (code lo, code hi, x, y, z, m, original index) of a sorted shard / bucket."""
+    def _rec(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def phase_ms(self):
+        """CUDA-event time of the build phases of the last build() on this rank."""
+        self.torch.cuda.synchronize()
+        return {self._ev[i][0]: self._ev[i - 1][1].elapsed_time(self._ev[i][1]) for i in range(1, len(self._ev))}
+
+    def _sorted_arrays(self, t, n):
+        """codes, x, y, z, m, last_perm of a sorted shard / bucket as contiguous device tensors."""
         torch = self.torch
-        rows = torch.empty((n, 7), dtype=torch.int32, device=self.dev)
         codes = torch.empty(n, dtype=torch.int64, device=self.dev)
         cols = [torch.empty(n, dtype=self.dt, device=self.dev) for _ in range(4)]
         lp = torch.empty(n, dtype=torch.int32, device=self.dev)
         t.codes_device(codes)
         t.parts_device(*cols)
         t.perm_device(lp, RK_LAST_PERM)
-        rows[:, 0:2] = codes.view(torch.int32).reshape(n, 2)
-        for j in range(4):
-            rows[:, 2 + j] = cols[j].view(torch.int32)
-        rows[:, 6] = (lp + offset) if gidx is None else gidx[lp.long()]
-        return rows
+        return (codes, *cols, lp)
 
-    def _cols(self, rows):
-        torch = self.torch
-        n = rows.shape[0]
-        codes = rows[:, 0:2].contiguous().view(torch.int64).reshape(n)
-        x, y, z, m = (rows[:, 2 + j].contiguous().view(self.dt) for j in range(4))
-        return codes, x, y, z, m, rows[:, 6].contiguous()
+    def _persistent(self, key, n, dtype):
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = self.torch.empty(int(n * 1.02) + 16, dtype=dtype, device=self.dev)
+            self._bufs[key] = buf
+        return buf[:n]
+
+    def _allgather_uneven(self, mine, offs, full=None, copy_in=False):
+        """All-gather of unequal contiguous slices: rank r owns full[offs[r]:offs[r+1]]. One grouped NCCL
+        send/recv round (every pair exchanges directly over NVLink), no padding and no staging copies."""
+        torch, dist = self.torch, self.dist
+        if full is None or copy_in:
+            if full is None:
+                full = torch.empty(int(offs[-1]), dtype=mine.dtype, device=self.dev)
+            full[int(offs[self.rank]):int(offs[self.rank + 1])] = mine
+            mine = full[int(offs[self.rank]):int(offs[self.rank + 1])]
+        ops = []
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            if mine.numel():
+                ops.append(dist.P2POp(dist.isend, mine, r))
+            if offs[r + 1] > offs[r]:
+                ops.append(dist.P2POp(dist.irecv, full[int(offs[r]):int(offs[r + 1])], r))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return full
 
     # ---- traversal -----------------------------------------------------------------------------------------
     def _ensure_cuts(self):
@@ -127,8 +180,8 @@ class ShardedTree:
         self.tree.acc_pot(Q, theta, G=G, eps=eps, out=out, where=RK_DEVICE, crit_range=(c0, c1))
         info = self.tree.eval_info.asdict()
         if exchange:
-            # every rank owns one contiguous slice: zero the rest and sum (x + 0 is exact), one collective per
-            # output array instead of world x broadcasts
+            # every rank owns one contiguous slice of the Morton-ordered result
+            # zero everything this rank does not own and sum: x + 0 is exact, one tuned collective per array
             pb, pe = int(self.cut_particles[self.rank]), int(self.cut_particles[self.rank + 1])
             for o in out:
                 o[:pb].zero_()
@@ -136,9 +189,20 @@ class ShardedTree:
                 self.dist.all_reduce(o)
         return info
 
-    def rebalance(self):
-        """Cost-weighted cuts from the last evaluation's per-group interaction counts."""
-        costs = sharding.allreduce_costs(self.tree.group_costs(), self.dist, self.dev)
+    def rebalance(self, kernel_ms=None):
+        """Cost-weighted cuts from the last evaluation's per-group interaction counts. With kernel_ms (this rank's
+        traversal time of that evaluation) the counts of every rank's range are rescaled by its measured time per
+        interaction, so that ranges whose groups run at lower lane utilisation get fewer of them."""
+        torch = self.torch
+        local = self.tree.group_costs().astype(np.float64)
+        if kernel_ms is not None and self.cuts is not None:
+            c0, c1 = self.cuts[self.rank], self.cuts[self.rank + 1]
+            tot = local[c0:c1].sum()
+            if tot > 0:
+                local[c0:c1] *= kernel_ms * 1e6 / tot  # cost unit: nanoseconds of this rank
+        t = torch.from_numpy(local).to(self.dev)
+        self.dist.all_reduce(t)
+        costs = t.cpu().numpy()
         self.cuts = sharding.cuts_by_cost(costs, self.world)
         self.cut_particles = None
         return sharding.imbalance(costs, self.cuts)
