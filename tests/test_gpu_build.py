@@ -150,3 +150,61 @@ def test_full_size_properties(oracle_mod, rk):
     last = codes[nd["end"] - np.uint64(1)] >> sh
     want = nd["code"] - (np.uint64(1) << (np.uint64(3) * lvl))
     assert (first == want).all() and (last == want).all()
+
+
+def test_sample_sort_building_blocks_single_device(oracle_mod, rk):
+    """The multi-GPU build on ONE device: two shards are sorted with the global box
+    (rk_tree_sort_shard), merged through splitter buckets on the host, each bucket is sorted again with the
+    received codes, and rk_tree_build_presorted builds the tree from the concatenated buckets. The result must
+    be identical to the direct build (codes, perm, nodes, critical nodes)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    N = 150000
+    m, x, y, z = oracle_mod.plummer(N)
+    ref = rk.Octree()
+    ref.build(x, y, z, m)
+    box = ref.box_size
+    assert rk.deduce_box(float(max(np.abs(x).max(), np.abs(y).max(), np.abs(z).max())), 32) == box
+    cut = 70000
+    shards = []
+    for lo, hi in ((0, cut), (cut, N)):
+        t = rk.Octree()
+        d = [torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev) for a in (x, y, z, m)]
+        t.sort_shard(d[0], d[1], d[2], d[3], hi - lo, box)
+        codes = torch.empty(hi - lo, dtype=torch.int64, device=dev)
+        cols = [torch.empty(hi - lo, dtype=torch.float32, device=dev) for _ in range(4)]
+        lp = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+        t.codes_device(codes)
+        t.parts_device(*cols)
+        t.perm_device(lp, rk.RK_LAST_PERM)
+        shards.append((codes, cols, lp + lo))
+    split = int(np.median(ref.codes()))
+    buckets = []
+    for b in range(2):
+        sel = [(c < split) if b == 0 else (c >= split) for c, _, _ in shards]
+        bc = torch.cat([c[s] for (c, _, _), s in zip(shards, sel)])
+        bcols = [torch.cat([cols[j][s] for (_, cols, _), s in zip(shards, sel)]) for j in range(4)]
+        bi = torch.cat([g[s] for (_, _, g), s in zip(shards, sel)])
+        t = rk.Octree()
+        t.sort_shard(bcols[0], bcols[1], bcols[2], bcols[3], bc.numel(), box, codes=bc)
+        lp = torch.empty(bc.numel(), dtype=torch.int32, device=dev)
+        t.perm_device(lp, rk.RK_LAST_PERM)
+        sc = torch.empty_like(bc)
+        scols = [torch.empty_like(c) for c in bcols]
+        t.codes_device(sc)
+        t.parts_device(*scols)
+        buckets.append((sc, scols, bi[lp.long()]))
+    fc = torch.cat([b[0] for b in buckets])
+    fcols = [torch.cat([b[1][j] for b in buckets]) for j in range(4)]
+    fi = torch.cat([b[2] for b in buckets]).to(torch.int32)
+    g = rk.Octree()
+    g.build_presorted(fcols[0], fcols[1], fcols[2], fcols[3], fc, fi, N, box)
+    assert (g.codes() == ref.codes()).all()
+    assert (g.perm(0) == ref.perm(0)).all()
+    assert (g.perm(2) == ref.perm(2)).all()
+    assert (g.nodes() == ref.nodes()).all()
+    assert (g.crit() == ref.crit()).all()
+    a, b = g.acc_pot(0, 0.75, ordered=True), ref.acc_pot(0, 0.75, ordered=True)
+    for j in range(3):
+        assert (a[j] == b[j]).all()
+    assert (g.crit_begin_at([0, g.ncrit_nodes]) == [0, N]).all()
