@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) pack_absmax_kernel(const F *__restrict__ 
     u64 mx = 0;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const F a = x[i], b = y[i], c = z[i];
-        out[i] = make_vec4<F>(a, b, c, m[i]);
+        out[i] = make_vec4<F>(a, b, c, m ? m[i] : F(0)); // NULL masses arrive with the gather (late_m)
         const u64 ba = abs_bits(a), bb = abs_bits(b), bc = abs_bits(c);
         mx = ba > mx ? ba : mx;
         mx = bb > mx ? bb : mx;
@@ -192,11 +192,17 @@ __global__ void __launch_bounds__(256)
 
 template <typename F>
 __global__ void __launch_bounds__(256)
-    gather_kernel(const vec4<F> *__restrict__ pin, const u32 *__restrict__ idx, vec4<F> *__restrict__ pout, size_t n)
+    gather_kernel(const vec4<F> *__restrict__ pin, const u32 *__restrict__ idx, vec4<F> *__restrict__ pout, size_t n,
+                  const F *__restrict__ late_m)
 {
     const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
     if (i < n) {
-        pout[i] = pin[idx[i]];
+        const u32 j = idx[i];
+        vec4<F> v = pin[j];
+        if (late_m) { // masses whose upload overlapped the sort
+            v.w = late_m[j];
+        }
+        pout[i] = v;
     }
 }
 
@@ -978,10 +984,10 @@ void launch_encode(const vec4<F> *p, u64 *codes, size_t n, F inv_box, dev_error 
     }
 }
 template <typename F>
-void launch_gather(const vec4<F> *pin, const u32 *idx, vec4<F> *pout, size_t n, cudaStream_t st)
+void launch_gather(const vec4<F> *pin, const u32 *idx, vec4<F> *pout, size_t n, cudaStream_t st, const F *late_m)
 {
     if (n) {
-        gather_kernel<F><<<div_up(n, 256), 256, 0, st>>>(pin, idx, pout, n); count_launch();
+        gather_kernel<F><<<div_up(n, 256), 256, 0, st>>>(pin, idx, pout, n, late_m); count_launch();
     }
 }
 void launch_perm_invert(const u32 *perm, u32 *inv_perm, size_t n, cudaStream_t st)
@@ -1115,7 +1121,7 @@ void launch_export_crit(const u64 *codes, const uint4 *nodeB, const u32 *crit_no
                                        cudaStream_t);                                                                  \
     template void launch_unpack<F>(const vec4<F> *, F *, F *, F *, F *, size_t, cudaStream_t);                         \
     template void launch_encode<F>(const vec4<F> *, u64 *, size_t, F, dev_error *, cudaStream_t);                      \
-    template void launch_gather<F>(const vec4<F> *, const u32 *, vec4<F> *, size_t, cudaStream_t);                     \
+    template void launch_gather<F>(const vec4<F> *, const u32 *, vec4<F> *, size_t, cudaStream_t, const F *);          \
     template void topology_count<F>(build_arrays<F> &, size_t, size_t, cudaStream_t);                                  \
     template void topology_emit<F>(build_arrays<F> &, cudaStream_t);                                                   \
     template void node_properties<F>(build_arrays<F> &, int, F, cudaStream_t);                                         \

@@ -71,7 +71,7 @@ public:
         m_b.d_err.reserve(2);
         m_b.d_misc.reserve(8);
         m_counters.reserve(8);
-        m_work.reserve(4);
+        m_work.reserve(8);
     }
     ~tree()
     {
@@ -86,6 +86,16 @@ public:
         }
         if (m_own_stream) {
             cudaStreamDestroy(m_own_stream);
+        }
+        if (m_copy_stream) {
+            cudaStreamDestroy(m_copy_stream);
+            for (auto &s : m_aux_stream) {
+                cudaStreamDestroy(s);
+            }
+            for (auto &e : m_chunk_ev) {
+                cudaEventDestroy(e);
+            }
+            cudaEventDestroy(m_copy_ev);
         }
     }
     void use() const { RK_CUDA_CHECK(cudaSetDevice(m_device)); }
@@ -117,6 +127,7 @@ public:
         m_box_deduced = false;
         m_max_group = 0;
         m_costs_valid = false;
+        m_cuts_valid = false;
         m_h_crit_begin.clear();
     }
 
@@ -153,11 +164,29 @@ public:
             reserve_particles(n);
             RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[0], m_stream));
             const F *dx, *dy, *dz, *dm;
-            upload4(x, y, z, m, n, where, dx, dy, dz, dm);
+            m_late_m = nullptr;
+            if (where == RK_HOST && m && n >= (size_t(1) << 20)) {
+                // Host input: the coordinates are needed at once (box, codes), the masses only when the particles
+                // are permuted, so their upload runs on the copy stream underneath the encode and the sort.
+                upload4(x, y, z, nullptr, n, where, dx, dy, dz, dm);
+                ensure_copy_stream();
+                m_b.stage[3].reserve(n, 1.05);
+                RK_CUDA_CHECK(cudaEventRecord(m_chunk_ev[0], m_stream)); // behind x, y, z on the link, not beside them
+                RK_CUDA_CHECK(cudaStreamWaitEvent(m_copy_stream, m_chunk_ev[0], 0));
+                RK_CUDA_CHECK(cudaMemcpyAsync(m_b.stage[3].p, m, n * sizeof(F), cudaMemcpyHostToDevice, m_copy_stream));
+                RK_CUDA_CHECK(cudaEventRecord(m_copy_ev, m_copy_stream));
+                m_late_m = m_b.stage[3].p;
+            } else {
+                upload4(x, y, z, m, n, where, dx, dy, dz, dm);
+            }
             reset_flags();
             launch_pack_absmax<F>(dx, dy, dz, dm, m_b.pin.p, n, reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
             rebuild(true, info);
         } catch (...) {
+            if (m_late_m) { // do not leave an upload from the caller's buffer in flight
+                cudaStreamSynchronize(m_copy_stream);
+                m_late_m = nullptr;
+            }
             clear();
             throw;
         }
@@ -585,7 +614,7 @@ public:
             }
         }
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[4], m_stream));
-        RK_CUDA_CHECK(cudaMemsetAsync(m_work.p, 0, 4 * sizeof(u32), m_stream));
+        RK_CUDA_CHECK(cudaMemsetAsync(m_work.p, 0, 8 * sizeof(u32), m_stream));
         RK_CUDA_CHECK(cudaMemsetAsync(m_counters.p, 0, 8 * sizeof(u64), m_stream));
         const bool partial = (c0 != 0 || c1 != C);
         if (partial && ordered && where == RK_HOST) {
@@ -594,8 +623,6 @@ public:
             }
         }
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
-        launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream);
-        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
         // particle range covered by [c0, c1)
         size_t pb = 0, pe = n;
         if (partial) {
@@ -603,15 +630,77 @@ public:
             pb = m_h_crit_begin[c0];
             pe = m_h_crit_begin[c1];
         }
-        if (where == RK_HOST) {
-            for (int j = 0; j < nres; ++j) {
-                if (ordered) {
-                    RK_CUDA_CHECK(cudaMemcpyAsync(out[j], p.out[j], n * sizeof(F), cudaMemcpyDeviceToHost, m_stream));
-                } else {
-                    RK_CUDA_CHECK(cudaMemcpyAsync(static_cast<F *>(out[j]) + pb, p.out[j] + pb, (pe - pb) * sizeof(F),
-                                                  cudaMemcpyDeviceToHost, m_stream));
+        unsigned launches = 1;
+        const bool pipelined = where == RK_HOST && !ordered && (pe - pb) >= (size_t(1) << 20);
+        if (!pipelined) {
+            launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream);
+            RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
+            if (where == RK_HOST) {
+                for (int j = 0; j < nres; ++j) {
+                    if (ordered) {
+                        RK_CUDA_CHECK(
+                            cudaMemcpyAsync(out[j], p.out[j], n * sizeof(F), cudaMemcpyDeviceToHost, m_stream));
+                    } else {
+                        RK_CUDA_CHECK(cudaMemcpyAsync(static_cast<F *>(out[j]) + pb, p.out[j] + pb,
+                                                      (pe - pb) * sizeof(F), cudaMemcpyDeviceToHost, m_stream));
+                    }
                 }
             }
+        } else {
+            // Host outputs in Morton order: cut the critical nodes into NCHUNK launches (40/30/20/10 %) on separate
+            // streams - the CTAs of launch k+1 fill the SMs as those of launch k drain, so there is one tail, not
+            // NCHUNK - and copy each launch's contiguous output range back on the copy stream as soon as that launch
+            // has finished. Only the last tenth of the device-to-host traffic is exposed.
+            ensure_copy_stream();
+            const size_t nc = c1 - c0;
+            size_t cuts[NCHUNK + 1], pcut[NCHUNK + 1];
+            cuts[0] = c0, cuts[NCHUNK] = c1, pcut[0] = pb, pcut[NCHUNK] = pe;
+            if (!partial && m_cuts_valid) {
+                for (int k = 1; k < NCHUNK; ++k) {
+                    cuts[k] = m_cut_crit[k - 1];
+                    pcut[k] = m_cut_begin[k - 1];
+                }
+            } else {
+                host_crit_begin();
+                for (int k = 1; k < NCHUNK; ++k) {
+                    cuts[k] = c0 + nc * chunk_mark(k) / 10;
+                    pcut[k] = m_h_crit_begin[cuts[k]];
+                }
+            }
+            launches = 0;
+            for (int k = 0; k < NCHUNK; ++k) {
+                if (cuts[k + 1] == cuts[k]) {
+                    continue;
+                }
+                cudaStream_t st = k ? m_aux_stream[k - 1] : m_stream;
+                if (k) {
+                    RK_CUDA_CHECK(cudaStreamWaitEvent(st, m_ev.ev[5], 0));
+                }
+                trav_params<F> q = p;
+                q.c0 = static_cast<u32>(cuts[k]);
+                q.c1 = static_cast<u32>(cuts[k + 1]);
+                q.work_counter = m_work.p + 4 + k; // one work counter per launch
+                launch_traverse<F>(q, Q, m_mac, m_sm_count, st);
+                RK_CUDA_CHECK(cudaEventRecord(m_chunk_ev[k], st));
+                ++launches;
+            }
+            for (int k = 0; k < NCHUNK; ++k) {
+                if (cuts[k + 1] == cuts[k]) {
+                    continue;
+                }
+                if (k) {
+                    RK_CUDA_CHECK(cudaStreamWaitEvent(m_stream, m_chunk_ev[k], 0));
+                }
+                const size_t b = pcut[k], e = pcut[k + 1];
+                RK_CUDA_CHECK(cudaStreamWaitEvent(m_copy_stream, m_chunk_ev[k], 0));
+                for (int j = 0; j < nres; ++j) {
+                    RK_CUDA_CHECK(cudaMemcpyAsync(static_cast<F *>(out[j]) + b, p.out[j] + b, (e - b) * sizeof(F),
+                                                  cudaMemcpyDeviceToHost, m_copy_stream));
+                }
+            }
+            RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream)); // all launches done
+            RK_CUDA_CHECK(cudaEventRecord(m_copy_ev, m_copy_stream));
+            RK_CUDA_CHECK(cudaStreamWaitEvent(m_stream, m_copy_ev, 0)); // the tree's stream sees the copies
         }
         RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
         RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 8, m_work.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
@@ -628,7 +717,7 @@ public:
             info->p2p_pairs = m_hpin[2];
             info->self_pairs = m_hpin[3];
             info->n_groups = c1 - c0;
-            info->kernel_launches = 1;
+            info->kernel_launches = launches;
             RK_CUDA_CHECK(cudaEventElapsedTime(&info->ms_kernel, m_ev.ev[5], m_ev.ev[6]));
             RK_CUDA_CHECK(cudaEventElapsedTime(&info->ms_total, m_ev.ev[4], m_ev.ev[7]));
             // interactions = sum over groups of T*(leaf sources + accepted) + T*(T-1)
@@ -944,7 +1033,11 @@ private:
         m_b.last_perm = lperm;
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[2], m_stream));
         // ---- permute ----
-        launch_gather<F>(m_b.pin.p, lperm, m_b.psorted.p, n, m_stream);
+        if (m_late_m) {
+            RK_CUDA_CHECK(cudaStreamWaitEvent(m_stream, m_copy_ev, 0));
+        }
+        launch_gather<F>(m_b.pin.p, lperm, m_b.psorted.p, n, m_stream, m_late_m);
+        m_late_m = nullptr;
         if (first) {
             launch_perm_first(lperm, m_b.perm.p, nullptr, n, m_stream);
         } else {
@@ -1010,9 +1103,21 @@ private:
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
         RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_err.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
         RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 2, m_b.d_misc.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+        // first particles of the critical nodes at the 40/70/90 % marks: where acc_pot() cuts a host-output
+        // evaluation into pipelined launches (read back here so that the evaluation needs no extra sync)
+        u32 *hcut = reinterpret_cast<u32 *>(m_hpin + 4);
+        for (int k = 0; k < NCHUNK - 1; ++k) {
+            m_cut_crit[k] = C * chunk_mark(k + 1) / 10;
+            RK_CUDA_CHECK(cudaMemcpyAsync(hcut + k, m_b.crit_begin.p + m_cut_crit[k], sizeof(u32),
+                                          cudaMemcpyDeviceToHost, m_stream));
+        }
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
         check_props_error(m_hpin[1]);
         m_max_group = reinterpret_cast<const u32 *>(m_hpin + 2)[2];
+        for (int k = 0; k < NCHUNK - 1; ++k) {
+            m_cut_begin[k] = hcut[k];
+        }
+        m_cuts_valid = true;
         m_costs_valid = false;
         m_have_inv = false;
         m_h_crit_begin.clear();
@@ -1078,6 +1183,19 @@ private:
         throw api_error(RK_ERR_INVALID_ARGUMENT, "The computation of the distance between the centre of mass "
                                                  "and the geometric centre of a node produced the non-finite value inf");
     }
+    void ensure_copy_stream()
+    {
+        if (!m_copy_stream) {
+            RK_CUDA_CHECK(cudaStreamCreateWithFlags(&m_copy_stream, cudaStreamNonBlocking));
+            for (auto &s : m_aux_stream) {
+                RK_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            }
+            for (auto &e : m_chunk_ev) {
+                RK_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
+            RK_CUDA_CHECK(cudaEventCreateWithFlags(&m_copy_ev, cudaEventDisableTiming));
+        }
+    }
     void host_crit_begin()
     {
         if (m_h_crit_begin.size() == m_b.n_crit + 1) {
@@ -1090,7 +1208,14 @@ private:
     }
 
     int m_mac, m_device, m_sm_count = 148;
-    cudaStream_t m_stream = nullptr, m_own_stream = nullptr;
+    cudaStream_t m_stream = nullptr, m_own_stream = nullptr, m_copy_stream = nullptr;
+    static constexpr int NCHUNK = 4; // pipelined host-output evaluation: launches of 40/30/20/10 % of the groups
+    static constexpr size_t chunk_mark(int k) { return k == 1 ? 4 : k == 2 ? 7 : 9; } // tenths
+    cudaStream_t m_aux_stream[NCHUNK - 1] = {};
+    cudaEvent_t m_chunk_ev[NCHUNK] = {}, m_copy_ev = nullptr;
+    const F *m_late_m = nullptr;
+    size_t m_cut_crit[NCHUNK - 1] = {}, m_cut_begin[NCHUNK - 1] = {};
+    bool m_cuts_valid = false;
     timer_events m_ev;
     build_arrays<F> m_b;
     sort_scratch m_sc;

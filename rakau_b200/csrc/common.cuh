@@ -198,7 +198,8 @@ void launch_set_coords(vec4<F> *p, const F *x, const F *y, const F *z, const F *
 template <typename F>
 void launch_encode(const vec4<F> *p, u64 *codes, size_t n, F inv_box, dev_error *err, cudaStream_t st);
 template <typename F>
-void launch_gather(const vec4<F> *pin, const u32 *idx, vec4<F> *pout, size_t n, cudaStream_t st);
+void launch_gather(const vec4<F> *pin, const u32 *idx, vec4<F> *pout, size_t n, cudaStream_t st,
+                   const F *late_m = nullptr);
 void launch_perm_invert(const u32 *perm, u32 *inv_perm, size_t n, cudaStream_t st);
 void launch_perm_first(const u32 *last_perm, u32 *perm, u32 *inv_perm, size_t n, cudaStream_t st);
 void launch_perm_compose(const u32 *old_perm, const u32 *last_perm, u32 *new_perm, u32 *inv_perm, size_t n,

@@ -264,3 +264,41 @@ def test_external_tree_split_offset(oracle_mod, rk):
         assert np.median(rel) <= 1e-6
     with pytest.raises(rk.RakauError):
         rk.traverse_external_tree(o.nodes(), o.parts(), o.codes(), 2, mv, first=first + 1)
+
+
+def test_pipelined_host_path_matches_device_path(oracle_mod, rk):
+    """n >= 2^20 with host buffers takes the pipelined route (masses uploaded underneath the sort, four traversal
+    launches with overlapped device-to-host copies): results, permutation and counters must be bit-identical to
+    the single-launch device-buffer route, and the masses must land on the right particles."""
+    import torch
+    n = (1 << 20) + 12345
+    m, x, y, z = oracle_mod.plummer(n)
+    m = (m * (1.0 + np.arange(n, dtype=np.float32) / n)).astype(np.float32)  # distinct masses
+    gh = rk.Octree()
+    gh.build(x, y, z, m)
+    host = gh.acc_pot(2, 0.75, eps=0.001)
+    ih = gh.eval_info.asdict()
+    assert ih["kernel_launches"] == 4
+    gd = rk.Octree()
+    dev = [torch.from_numpy(a).cuda() for a in (x, y, z, m)]
+    gd.build(*dev, where=rk.RK_DEVICE, n=n)
+    out = [torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(4)]
+    gd.acc_pot(2, 0.75, eps=0.001, out=out, where=rk.RK_DEVICE)
+    idv = gd.eval_info.asdict()
+    assert idv["kernel_launches"] == 1
+    torch.cuda.synchronize()
+    for k in COUNT_KEYS:
+        assert ih[k] == idv[k], k
+    assert (gh.perm(0) == gd.perm(0)).all()
+    for a, b in zip(gh.parts(), gd.parts()):
+        assert (a == b).all()
+    assert (gh.parts()[3] == m[gh.perm(0).astype(np.int64)]).all()
+    for j in range(4):
+        assert (host[j] == out[j].cpu().numpy()).all(), j
+    # a ranged host evaluation large enough to be pipelined as well
+    C = gh.ncrit_nodes
+    part = [np.full(n, np.nan, dtype=np.float32) for _ in range(4)]
+    gh.acc_pot(2, 0.75, eps=0.001, out=part, crit_range=(3, C))
+    lo = int(gh.crit_begin_at([3])[0])
+    for j in range(4):
+        assert (part[j][lo:] == host[j][lo:]).all() and np.isnan(part[j][:lo]).all()
