@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librakau_b200.so")
+LIB_PATH = os.environ.get("RK_LIB") or os.path.join(_HERE, "lib", "librakau_b200.so")  # RK_LIB: tuning builds
 _LIB = None
 
 RK_HOST, RK_DEVICE = 0, 1

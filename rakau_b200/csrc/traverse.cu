@@ -37,7 +37,21 @@ namespace
 
 constexpr int TRAV_WARPS = 4;
 constexpr int TRAV_THREADS = TRAV_WARPS * 32;
-constexpr int LCAP = 64;         // source ring capacity: two 32-entry blocks (batch being filled + scratch)
+#ifndef RK_UNROLL
+#define RK_UNROLL 4
+#endif
+#ifndef RK_AMB2
+#define RK_AMB2 1
+#endif
+#ifndef RK_CTAS
+#define RK_CTAS 5
+#endif
+#define RK_PRAGMA_(x) _Pragma(#x)
+#define RK_UNROLL_PRAGMA(n) RK_PRAGMA_(unroll n)
+// BATCH (template parameter of the kernel) = sources evaluated per consume step; the source ring holds 2 * BATCH
+// entries: the batch being filled + room for one step's appends / scratch. 64 amortises the per-batch accumulator
+// round trip through shared memory better than 32 (-6 % kernel time at ncrit = 128); 32 is kept for the large
+// tmax configurations where the bigger ring would cost a resident CTA (chosen in launch_one()).
 constexpr int STACK_CAP = 512;   // (first child, count) entries per warp (<= 32 pushes per step, depth <= 21)
 constexpr u32 FULL = 0xffffffffu;
 
@@ -123,7 +137,7 @@ __device__ __forceinline__ void eval_tile(const vec4<F> *__restrict__ src, u32 j
         ap[w] = a.w;
         self_idx[w] = ti;
     }
-#pragma unroll 4
+RK_UNROLL_PRAGMA(RK_UNROLL)
     for (u32 j = jb; j < je; ++j) {
         const vec4<F> s = src[j];
 #pragma unroll
@@ -176,19 +190,20 @@ __device__ __forceinline__ void eval_slots(const vec4<F> *__restrict__ src, u32 
 }
 
 template <typename F>
-__host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax)
+__host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax, u32 LCAP)
 {
     // ring + staged targets + accumulators (1.5 * tmax entries: up to 1.5*tmax/32 slots per lane) + stack + queues
     return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(tmax + tmax / 2) * sizeof(vec4<F>)
            + size_t(STACK_CAP) * 4 + 32 * 4 /*nodebuf*/ + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
 }
 
-template <typename F, int Q, int MAC>
-__global__ void __launch_bounds__(TRAV_THREADS, 5) traverse_kernel(const trav_params<F> p)
+template <typename F, int Q, int MAC, int BATCH_>
+__global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const trav_params<F> p)
 {
+    constexpr u32 BATCH = BATCH_, LCAP = 2 * BATCH_;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *base = smem_raw + size_t(warp) * warp_smem_bytes<F>(p.tmax);
+    unsigned char *base = smem_raw + size_t(warp) * warp_smem_bytes<F>(p.tmax, LCAP);
     vec4<F> *ring = reinterpret_cast<vec4<F> *>(base);
     vec4<F> *tgt = ring + LCAP;
     vec4<F> *acc = tgt + p.tmax;
@@ -283,7 +298,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 5) traverse_kernel(const trav_pa
 
             for (;;) {
                 // ---------------- produce: fill the ring until >= 32 sources or the walk is over -------------
-                while (lcount < 32u && !done) {
+                while (lcount < BATCH && !done) {
                     if (lq_done < lq_total) {
                         // copy more particles of the rejected leaves into the ring
                         const u32 room = LCAP - lcount, rem = lq_total - lq_done;
@@ -369,12 +384,33 @@ __global__ void __launch_bounds__(TRAV_THREADS, 5) traverse_kernel(const trav_pa
                             // the 32 lanes share the targets of ONE node at a time (broadcast LDS.128 per node)
                             const u32 m_need = __ballot_sync(FULL, need);
                             const u32 n_need = __popc(m_need), my_slot = __popc(m_need & ltm);
-                            vec4<F> *amb = ring + ((lhead + 32u) & (LCAP - 1)); // a free 32-entry block (lcount < 32 here)
+                            vec4<F> *amb = ring + ((lhead + BATCH) & (LCAP - 1)); // a free 32-entry block (lcount < BATCH here)
                             if (need) {
                                 amb[my_slot] = make_vec4<F>(na.x, na.y, na.z, mac_lh);
                             }
                             __syncwarp();
                             u32 fail_bits = 0;
+#if RK_AMB2
+                            // two nodes per pass: each half-warp shares the targets of one node
+                            const u32 half = static_cast<u32>(lane) >> 4, hl = static_cast<u32>(lane) & 15u;
+#pragma unroll 1
+                            for (u32 a = 0; a < n_need; a += 2u) {
+                                const vec4<F> c = amb[a + half < n_need ? a + half : a];
+                                bool f = false;
+#pragma unroll 1
+                                for (u32 i = hl; i < T; i += 16) {
+                                    const vec4<F> t = tgt[i];
+                                    const F dx = rn_sub(c.x, t.x), dy = rn_sub(c.y, t.y), dz = rn_sub(c.z, t.z);
+                                    F d2 = rn_mul(dx, dx);
+                                    d2 = rn_fma(dy, dy, d2);
+                                    d2 = rn_fma(dz, dz, d2);
+                                    f = f || (c.w >= d2);
+                                }
+                                const u32 fb = __ballot_sync(FULL, f);
+                                fail_bits |= ((fb & 0xffffu) ? 1u : 0u) << a;
+                                fail_bits |= ((fb >> 16) && a + 1u < n_need ? 1u : 0u) << (a + 1u);
+                            }
+#else
 #pragma unroll 1
                             for (u32 a = 0; a < n_need; ++a) {
                                 const vec4<F> c = amb[a];
@@ -390,6 +426,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 5) traverse_kernel(const trav_pa
                                 }
                                 fail_bits |= __any_sync(FULL, f) ? (1u << a) : 0u;
                             }
+#endif
                             __syncwarp();
                             if (need) {
                                 fail = (fail_bits >> my_slot) & 1u;
@@ -450,7 +487,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 5) traverse_kernel(const trav_pa
                     break;
                 }
                 // ---------------- consume: evaluate up to 32 sources (the only ring call site) ----------------
-                const u32 ne = lcount < 32u ? lcount : 32u;
+                const u32 ne = lcount < BATCH ? lcount : BATCH;
                 eval_slots<F, Q, false>(ring + lhead, ne, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
                 __syncwarp();
                 lhead = (lhead + ne) & (LCAP - 1);
@@ -584,17 +621,32 @@ __global__ void __launch_bounds__(256) ffma_kernel(float *out, int iters, float 
     }
 }
 
+template <typename F, int Q, int MAC, int BATCH>
+int trav_occupancy(u32 tmax, size_t &smem)
+{
+    smem = warp_smem_bytes<F>(tmax, 2 * BATCH) * TRAV_WARPS;
+    int per_sm = 0;
+    if (cudaFuncSetAttribute(traverse_kernel<F, Q, MAC, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem))
+            != cudaSuccess
+        || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_kernel<F, Q, MAC, BATCH>, TRAV_THREADS, smem)
+               != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return per_sm;
+}
+
 template <typename F, int Q, int MAC>
 void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st)
 {
-    const size_t smem = warp_smem_bytes<F>(p.tmax) * TRAV_WARPS;
-    RK_CUDA_CHECK(cudaFuncSetAttribute(traverse_kernel<F, Q, MAC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    int per_sm = 0;
-    RK_CUDA_CHECK(
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_kernel<F, Q, MAC>, TRAV_THREADS, smem));
+    // batches of 64 sources unless the larger ring costs a resident CTA (tmax = 256)
+    size_t smem64 = 0, smem32 = 0;
+    const int occ64 = trav_occupancy<F, Q, MAC, 64>(p.tmax, smem64), occ32 = trav_occupancy<F, Q, MAC, 32>(p.tmax, smem32);
+    const bool big = occ64 >= occ32 && occ64 > 0;
+    int per_sm = big ? occ64 : occ32;
     if (per_sm < 1) {
-        per_sm = 1;
+        throw cuda_error(1, "the traversal kernel does not fit on this device");
     }
     const u32 ngroups = p.c1 - p.c0;
     u32 grid = static_cast<u32>(sm_count) * static_cast<u32>(per_sm); // persistent: a multiple of the SM count
@@ -605,7 +657,12 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st)
     if (grid == 0) {
         return;
     }
-    traverse_kernel<F, Q, MAC><<<grid, TRAV_THREADS, smem, st>>>(p); count_launch();
+    if (big) {
+        traverse_kernel<F, Q, MAC, 64><<<grid, TRAV_THREADS, smem64, st>>>(p);
+    } else {
+        traverse_kernel<F, Q, MAC, 32><<<grid, TRAV_THREADS, smem32, st>>>(p);
+    }
+    count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }
 
