@@ -169,12 +169,12 @@ RK_UNROLL_PRAGMA(RK_UNROLL)
 
 // All rr slots of this lane against the same sources: tiles of 4, 2, 1 slots.
 template <typename F, int Q, bool SELF>
-__device__ __forceinline__ void eval_slots(const vec4<F> *__restrict__ src, u32 cnt, u32 sl, u32 S, F eps2,
+__device__ __forceinline__ void eval_slots(const vec4<F> *__restrict__ src, u32 cnt, u32 sl, u32 ls, F eps2,
                                            const vec4<F> *__restrict__ tpos, u32 T, u32 t_lane, u32 P, u32 rr,
                                            vec4<F> *__restrict__ acc_lane)
 {
     // slice sl takes the contiguous chunk [sl * per, (sl + 1) * per) of the cnt sources
-    const u32 per = (cnt + S - 1u) / S, jb = sl * per < cnt ? sl * per : cnt, je = jb + per < cnt ? jb + per : cnt;
+    const u32 per = (cnt + (1u << ls) - 1u) >> ls, jb = sl * per < cnt ? sl * per : cnt, je = jb + per < cnt ? jb + per : cnt;
     u32 k = 0;
 #pragma unroll 1
     for (; k + 4u <= rr; k += 4u) {
@@ -189,11 +189,17 @@ __device__ __forceinline__ void eval_slots(const vec4<F> *__restrict__ src, u32 
     }
 }
 
+__host__ __device__ constexpr u32 acc_entries(u32 tmax)
+{
+    // accumulator entries per warp = 32 * (slots per lane). Slicing replicates the accumulators S times, so more
+    // entries let more groups use narrow slices without padding: 2 * tmax where it costs no resident CTA.
+    return tmax <= 128u ? 2u * tmax : tmax + tmax / 2u;
+}
 template <typename F>
 __host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax, u32 LCAP)
 {
-    // ring + staged targets + accumulators (1.5 * tmax entries: up to 1.5*tmax/32 slots per lane) + stack + queues
-    return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(tmax + tmax / 2) * sizeof(vec4<F>)
+    // ring + staged targets + accumulators + stack + queues
+    return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(acc_entries(tmax)) * sizeof(vec4<F>)
            + size_t(STACK_CAP) * 4 + 32 * 4 /*nodebuf*/ + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
 }
 
@@ -207,8 +213,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
     vec4<F> *ring = reinterpret_cast<vec4<F> *>(base);
     vec4<F> *tgt = ring + LCAP;
     vec4<F> *acc = tgt + p.tmax;
-    u32 *stack = reinterpret_cast<u32 *>(acc + p.tmax + p.tmax / 2);
-    const u32 rr_cap = (p.tmax + p.tmax / 2) / 32u; // accumulator slots per lane
+    u32 *stack = reinterpret_cast<u32 *>(acc + acc_entries(p.tmax));
+    const u32 rr_cap = acc_entries(p.tmax) / 32u; // accumulator slots per lane
     u32 *nodebuf = stack + STACK_CAP;
     u32 *lq_incl = nodebuf + 32;
     u32 *lq_base = lq_incl + 32;
@@ -296,19 +302,16 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
         for (u32 t0 = 0; t0 < T; t0 += 32u * rr_cap) {
             const u32 tc = (T - t0 < 32u * rr_cap) ? (T - t0) : 32u * rr_cap;
             // Slice the warp: P lanes per slice, S = 32/P slices, rr target slots per lane; minimise rr * P >= tc.
-            u32 P = 32u, rr = (tc + 31u) / 32u;
-            {
-                const u32 r16 = (tc + 15u) / 16u, r8 = (tc + 7u) / 8u;
-                if (r16 <= rr_cap && r16 * 16u < rr * P) {
-                    P = 16u;
-                    rr = r16;
-                }
-                if (r8 <= rr_cap && r8 * 8u < rr * P) {
-                    P = 8u;
-                    rr = r8;
+            u32 lp = 5u, rr = (tc + 31u) / 32u; // P = 1 << lp
+#pragma unroll
+            for (u32 l = 4u; l >= 2u; --l) {
+                const u32 r = (tc + (1u << l) - 1u) >> l;
+                if (r <= rr_cap && (r << l) < (rr << lp)) {
+                    lp = l;
+                    rr = r;
                 }
             }
-            const u32 S = 32u / P, sl = static_cast<u32>(lane) / P, tl = static_cast<u32>(lane) % P;
+            const u32 P = 1u << lp, sl = static_cast<u32>(lane) >> lp, tl = static_cast<u32>(lane) & (P - 1u);
             vec4<F> *acc_lane = acc + lane;
             for (u32 k = 0; k < rr; ++k) {
                 acc_lane[32u * k] = make_vec4<F>(F(0), F(0), F(0), F(0));
@@ -339,8 +342,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                             const u32 pidx = lq_base[lo] + f;
                             cp_async_vec4(&ring[(lhead + lcount + (f - lq_done)) & (LCAP - 1)], p.parts + pidx);
                         }
-                        cp_async_wait_all();
-                        __syncwarp();
+                        __syncwarp(); // (the copies stay in flight until the next consume step)
                         lcount += chunk;
                         lq_done += chunk;
                         continue;
@@ -508,6 +510,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     lq_done = 0;
                     if (m_leaf) {
                         const u32 c = open_leaf ? (nb.y - nb.x) : 0u;
+                        // queue the leaves (inclusive scan of their sizes); their particles are copied in ring-sized
+                        // chunks by the next iterations of the produce loop (a per-leaf copy loop measured no faster)
                         const u32 li = warp_incl_scan(c, lane);
                         lq_incl[lane] = li;
                         lq_base[lane] = nb.x - (li - c);
@@ -524,7 +528,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 }
                 // ---------------- consume: evaluate up to 32 sources (the only ring call site) ----------------
                 const u32 ne = lcount < BATCH ? lcount : BATCH;
-                eval_slots<F, Q, false>(ring + lhead, ne, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                cp_async_wait_all(); // leaf particles still in flight
+                __syncwarp();
+                eval_slots<F, Q, false>(ring + lhead, ne, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
                 __syncwarp();
                 lhead = (lhead + ne) & (LCAP - 1);
                 lcount -= ne;
@@ -535,9 +541,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
 
             // self interactions inside the group, tree.hpp:2073-2321 (sources = the group's own particles)
             if (staged) {
-                eval_slots<F, Q, true>(tgt, T, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                eval_slots<F, Q, true>(tgt, T, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
             } else {
-                eval_slots<F, Q, true>(gsrc, T, sl, S, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                eval_slots<F, Q, true>(gsrc, T, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
             }
 
             // Combine the slices' partial sums (fixed shuffle tree: deterministic), apply G as one final multiply
