@@ -43,6 +43,15 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #ifndef RK_AMB2
 #define RK_AMB2 1
 #endif
+#ifndef RK_PACKED
+#define RK_PACKED 1
+#endif
+#ifndef RK_NP4
+#define RK_NP4 0
+#endif
+#ifndef RK_SINGLE_SCALAR
+#define RK_SINGLE_SCALAR 1
+#endif
 #ifndef RK_CTAS
 #define RK_CTAS 5
 #endif
@@ -164,6 +173,146 @@ RK_UNROLL_PRAGMA(RK_UNROLL)
 #pragma unroll
     for (int w = 0; w < W; ++w) {
         acc[32 * w] = make_vec4<F>(ax[w], ay[w], az[w], ap[w]);
+    }
+}
+
+// ---- packed FP32 (sm_100a FFMA2 / FADD2 / FMUL2, PTX *.f32x2) ------------------------------------------------
+// One packed instruction performs two independent IEEE fp32 operations on a 64-bit register pair for ONE issue
+// slot (measured, tools/microbench/ffma2.cu: FFMA2 sustains the same 72 TFLOP/s as FFMA with half the issued
+// instructions). The traversal kernel is bound by issue slots (57 % FP32, 43 % walk/addressing/control), so the
+// fp32 interaction loop pairs two TARGETS of the lane in one register pair; the source components are scalar
+// registers which ptxas feeds through the instruction's broadcast operand form (FADD2 Rd, -Rt.F32x2, Rs.F32), so
+// the loop body is 1 LDS.128 + 12 packed instructions + 2 MUFU.RSQ per two interactions and no MOV.
+// Every lane-level operation is the same rn operation in the same order as the scalar loop: results are
+// bit-identical.
+__device__ __forceinline__ u64 pk2(float lo, float hi)
+{
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b)
+{
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// NP pairs of target slots (slots 2k and 2k+1 of the tile; SINGLE: one slot, paired with itself and the upper half
+// discarded) against the sources src[jb, je).
+template <int Q, int NP, bool SINGLE>
+__device__ __forceinline__ void eval_tile_packed(const float4 *__restrict__ src, u32 jb, u32 je, float eps2,
+                                                 const float4 *__restrict__ tpos, u32 T, u32 first_t, u32 P,
+                                                 float4 *__restrict__ acc)
+{
+    u64 tx[NP], ty[NP], tz[NP], ax[NP], ay[NP], az[NP], ap[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const u32 t0i = first_t + P * (2 * k), t1i = SINGLE ? t0i : first_t + P * (2 * k + 1);
+        // component-wise scalar loads straight into the two halves of each register pair (a float4 load would
+        // leave the halves in different quads and ptxas re-packs them with MOVs inside the loop)
+        const float *p0 = reinterpret_cast<const float *>(tpos + (t0i < T ? t0i : T - 1u)),
+                    *p1 = reinterpret_cast<const float *>(tpos + (t1i < T ? t1i : T - 1u));
+        const float4 a0 = acc[32 * (2 * k)], a1 = SINGLE ? a0 : acc[32 * (2 * k + 1)];
+        tx[k] = pk2(p0[0], p1[0]);
+        ty[k] = pk2(p0[1], p1[1]);
+        tz[k] = pk2(p0[2], p1[2]);
+        ax[k] = pk2(a0.x, a1.x);
+        ay[k] = pk2(a0.y, a1.y);
+        az[k] = pk2(a0.z, a1.z);
+        ap[k] = pk2(a0.w, a1.w);
+    }
+    const u64 e2 = pk2(eps2, eps2);
+RK_UNROLL_PRAGMA(RK_UNROLL)
+    for (u32 j = jb; j < je; ++j) {
+        const float4 s = src[j];
+        const u64 sx = pk2(s.x, s.x), sy = pk2(s.y, s.y), sz = pk2(s.z, s.z), sm = pk2(s.w, s.w);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const u64 dx = sub2(sx, tx[k]), dy = sub2(sy, ty[k]), dz = sub2(sz, tz[k]);
+            u64 d2 = fma2(dx, dx, e2);
+            d2 = fma2(dy, dy, d2);
+            d2 = fma2(dz, dz, d2);
+            float d2a, d2b;
+            upk2(d2, d2a, d2b);
+            const u64 inv = pk2(fast_rsqrt(d2a), fast_rsqrt(d2b));
+            if (Q != 1) {
+                const u64 ms = mul2(sm, mul2(mul2(inv, inv), inv));
+                ax[k] = fma2(dx, ms, ax[k]);
+                ay[k] = fma2(dy, ms, ay[k]);
+                az[k] = fma2(dz, ms, az[k]);
+            }
+            if (Q != 0) {
+                ap[k] = fma2(sm, inv, ap[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        float4 a0, a1;
+        upk2(ax[k], a0.x, a1.x);
+        upk2(ay[k], a0.y, a1.y);
+        upk2(az[k], a0.z, a1.z);
+        upk2(ap[k], a0.w, a1.w);
+        acc[32 * (2 * k)] = a0;
+        if (!SINGLE) {
+            acc[32 * (2 * k + 1)] = a1;
+        }
+    }
+}
+
+// fp32, non-self sources: all rr slots of this lane against the ring entries, two slots per register pair.
+template <int Q>
+__device__ __forceinline__ void eval_slots_packed(const float4 *__restrict__ src, u32 cnt, u32 sl, u32 ls, float eps2,
+                                                  const float4 *__restrict__ tpos, u32 T, u32 t_lane, u32 P, u32 rr,
+                                                  float4 *__restrict__ acc_lane)
+{
+    const u32 per = (cnt + (1u << ls) - 1u) >> ls, jb = sl * per < cnt ? sl * per : cnt, je = jb + per < cnt ? jb + per : cnt;
+    u32 k = 0;
+#if RK_NP4
+#pragma unroll 1
+    for (; k + 8u <= rr; k += 8u) {
+        eval_tile_packed<Q, 4, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+    }
+    if (k + 4u <= rr) {
+        eval_tile_packed<Q, 2, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        k += 4u;
+    }
+#else
+#pragma unroll 1
+    for (; k + 4u <= rr; k += 4u) {
+        eval_tile_packed<Q, 2, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+    }
+#endif
+    if (k + 2u <= rr) {
+        eval_tile_packed<Q, 1, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        k += 2u;
+    }
+    if (k < rr) {
+#if RK_SINGLE_SCALAR
+        eval_tile<float, Q, 1, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+#else
+        eval_tile_packed<Q, 1, true>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+#endif
     }
 }
 
@@ -530,7 +679,13 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 const u32 ne = lcount < BATCH ? lcount : BATCH;
                 cp_async_wait_all(); // leaf particles still in flight
                 __syncwarp();
-                eval_slots<F, Q, false>(ring + lhead, ne, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                if constexpr (sizeof(F) == 4 && RK_PACKED) {
+                    eval_slots_packed<Q>(reinterpret_cast<const float4 *>(ring + lhead), ne, sl, 5u - lp, eps2,
+                                         reinterpret_cast<const float4 *>(tpos), T, t0 + tl, P, rr,
+                                         reinterpret_cast<float4 *>(acc_lane));
+                } else {
+                    eval_slots<F, Q, false>(ring + lhead, ne, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                }
                 __syncwarp();
                 lhead = (lhead + ne) & (LCAP - 1);
                 lcount -= ne;
