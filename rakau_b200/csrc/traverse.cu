@@ -52,6 +52,12 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #ifndef RK_SINGLE_SCALAR
 #define RK_SINGLE_SCALAR 1
 #endif
+#ifndef RK_ACC15
+#define RK_ACC15 0
+#endif
+#ifndef RK_SKIP_EVAL
+#define RK_SKIP_EVAL 0
+#endif
 #ifndef RK_CTAS
 #define RK_CTAS 5
 #endif
@@ -61,7 +67,10 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 // entries: the batch being filled + room for one step's appends / scratch. 64 amortises the per-batch accumulator
 // round trip through shared memory better than 32 (-6 % kernel time at ncrit = 128); 32 is kept for the large
 // tmax configurations where the bigger ring would cost a resident CTA (chosen in launch_one()).
-constexpr int STACK_CAP = 512;   // (first child, count) entries per warp (<= 32 pushes per step, depth <= 21)
+#ifndef RK_STACK
+#define RK_STACK 512
+#endif
+constexpr int STACK_CAP = RK_STACK;   // (first child, count) entries per warp (<= 32 pushes per step, depth <= 21)
 constexpr u32 FULL = 0xffffffffu;
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
@@ -342,7 +351,11 @@ __host__ __device__ constexpr u32 acc_entries(u32 tmax)
 {
     // accumulator entries per warp = 32 * (slots per lane). Slicing replicates the accumulators S times, so more
     // entries let more groups use narrow slices without padding: 2 * tmax where it costs no resident CTA.
+#if RK_ACC15
+    return tmax + tmax / 2u;
+#else
     return tmax <= 128u ? 2u * tmax : tmax + tmax / 2u;
+#endif
 }
 template <typename F>
 __host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax, u32 LCAP)
@@ -679,7 +692,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 const u32 ne = lcount < BATCH ? lcount : BATCH;
                 cp_async_wait_all(); // leaf particles still in flight
                 __syncwarp();
-                if constexpr (sizeof(F) == 4 && RK_PACKED) {
+                if (RK_SKIP_EVAL && p.G != F(-12345)) {
+                    // timing experiment: walk only
+                } else if constexpr (sizeof(F) == 4 && RK_PACKED) {
                     eval_slots_packed<Q>(reinterpret_cast<const float4 *>(ring + lhead), ne, sl, 5u - lp, eps2,
                                          reinterpret_cast<const float4 *>(tpos), T, t0 + tl, P, rr,
                                          reinterpret_cast<float4 *>(acc_lane));
