@@ -464,11 +464,15 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
         for (u32 t0 = 0; t0 < T; t0 += 32u * rr_cap) {
             const u32 tc = (T - t0 < 32u * rr_cap) ? (T - t0) : 32u * rr_cap;
             // Slice the warp: P lanes per slice, S = 32/P slices, rr target slots per lane; minimise rr * P >= tc.
+            // Cost of a choice = slots + half a slot per lane when rr is odd: the fp32 loop evaluates two slots per
+            // packed instruction, an unpaired last slot runs the scalar loop at twice the issue cost.
             u32 lp = 5u, rr = (tc + 31u) / 32u; // P = 1 << lp
+            u32 best = (2u * rr + (rr & 1u)) << 5;
 #pragma unroll
             for (u32 l = 4u; l >= 2u; --l) {
-                const u32 r = (tc + (1u << l) - 1u) >> l;
-                if (r <= rr_cap && (r << l) < (rr << lp)) {
+                const u32 r = (tc + (1u << l) - 1u) >> l, cost = (2u * r + (r & 1u)) << l;
+                if (r <= rr_cap && cost < best) {
+                    best = cost;
                     lp = l;
                     rr = r;
                 }
