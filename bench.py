@@ -373,7 +373,7 @@ def run_ours(args):
                    "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"], "shard_cost_imbalance": state["imbalance"]},
         "ms_build": b_ms, "ms_traverse_kernel": k_ms,
         "build_phases_ms": {k: bi[k] for k in ("ms_encode", "ms_sort", "ms_permute", "ms_topology", "ms_props")},
-        "roofline": {"bound": "fp32", "kernel": "traverse_kernel<float,0,0>", "achieved": achieved,
+        "roofline": {"bound": "fp32", "kernel": "traverse_kernel<float,0,0,64>", "achieved": achieved,
                      "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
                      "convention": "12 FP32 issue slots per interaction counted as FMA (2 flop); peak = FFMA "
                                    "microbenchmark measured in this run",

@@ -6,25 +6,36 @@
 // tree_self_interactions 2073-2321, G scaling + write-out 2986-3007 — NOT the reference's per-particle
 // CUDA kernel (src/rakau_cuda.cu:152-335).
 //
-// Mapping: one warp owns one critical node (target group, <= ncrit particles). The group's targets live in
-// registers (R per lane) and, for the MAC test, in shared memory. The warp walks the level-major node array
-// with a shared-memory stack of (first child, count) entries: each step pops 32 nodes, ONE NODE PER LANE;
-// the lane evaluates the reference's group MAC (accepted iff mac_lh < dist2 for EVERY target, dist2
-// unsoftened, tree.hpp:2666-2672 / 2753) with exactly rounded operations so that decisions — and therefore
-// interaction counts — match the oracle. Accepted nodes' (com, mass) and the particles of rejected leaves
+// Mapping: one warp owns one critical node (target group, <= ncrit particles), persistent CTAs of 4 warps take
+// groups from an atomic counter. The group's targets are staged in shared memory; their accumulators live in
+// shared memory between batches and in registers (tiles of <= 4 targets per lane) inside a batch. The warp walks
+// the level-major node array with a shared-memory stack of (first child, count) entries: each step pops up to 4
+// entries = up to 32 nodes, ONE NODE PER LANE; the lane evaluates the reference's group MAC (accepted iff
+// mac_lh < dist2 for EVERY target, dist2 unsoftened, tree.hpp:2666-2672 / 2753) so that decisions - and therefore
+// interaction counts - match the oracle exactly. Accepted nodes' (com, mass) and the particles of rejected leaves
 // are appended (ballot + popc compaction; leaf particles staged with cp.async) to a shared-memory ring of
-// float4/double4 sources. Whenever the ring holds >= 32 sources the warp evaluates them against its
-// register-resident targets: broadcast LDS.128 per source, 3 FADD + 3 FFMA + MUFU.RSQ + 3 FMUL + 3 FFMA per
-// pair. Accumulation order is fixed by the tree, not by scheduling, so results are run-to-run
-// deterministic and G enters as one final multiply (reference test g_constant_acc.cpp:65-88).
+// float4/double4 sources; whenever the ring holds a batch (64 sources) the warp evaluates it against its targets.
+// Accumulation order is fixed by the tree, not by scheduling, so results are run-to-run deterministic and G
+// enters as one final multiply (reference test g_constant_acc.cpp:65-88).
 //
-// Two refinements found with ncu (profiles/r01_traverse_v1_*): (1) the per-target MAC loop was 26 % of all
-// issued instructions, so each lane first brackets the group MAC with the group's bounding box — if even the
-// nearest point of the box passes (or even the farthest fails) the decision is the reference's, exactly, and
-// the loop is skipped; only nodes inside the ~1e-6-wide guard band run the exact per-target loop;
-// (2) groups average 38 targets, so a warp is cut into S = 32/P slices of P lanes (P = 8, 16, 32 chosen per
-// group to minimise ceil(T/P)*P): every slice holds all targets (R per lane) and evaluates every S-th source,
-// partial sums are combined with a fixed shuffle tree at the end (lane utilisation 73 % -> 90 %).
+// What the ncu profiles under profiles/ led to (each step measured on the 4M Plummer workload, kernel time
+// 12.1 ms for the first version -> 4.84 ms):
+//  (1) MAC: the per-target loop was 26 % of all issued instructions. Each lane first lower-bounds dist2 with the
+//      group's bounding box (80 % of the tests end there: accepted), then tests ONE target with the reference's
+//      exactly rounded arithmetic - the group's support point towards the node, i.e. (almost always) its nearest
+//      target: if that one fails the node is rejected exactly as in the reference (18 %). Only the remaining 2 %
+//      run the exact loop over all targets, two nodes per pass (one per half-warp).
+//  (2) Lane utilisation: groups average 38 targets, so a warp is cut into S = 32/P slices of P lanes (P = 4..32
+//      chosen per group): every slice holds all targets (rr = ceil(T/P) per lane) and evaluates a contiguous
+//      1/S of each batch; partial sums are combined with a fixed shuffle tree at the end (slot padding 37 % -> 8 %).
+//  (3) Instruction cache: eight unrolled register-resident variants made a 136 KB kernel that spent 5.6 issue
+//      slots per instruction waiting on fetch; accumulators moved to shared memory, register tiles of 4/2/1.
+//  (4) Issue slots: fp32 interactions use the sm_100a packed instructions FFMA2/FADD2/FMUL2 (two targets per
+//      register pair, sources through the broadcast operand form), halving the FP32 instructions issued; slices
+//      are chosen so that the slot count per lane is even whenever that costs no padding.
+//  (5) Batches of 64 sources (was 32) amortise the accumulator round trip; 5 CTAs/SM (96 registers).
+// Measured dead ends are recorded in DESIGN.md (next-step node prefetch, per-leaf copy loops, 6 CTAs/SM,
+// 8-target register tiles).
 
 #include "common.cuh"
 #include "scan.cuh"
