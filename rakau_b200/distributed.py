@@ -9,7 +9,7 @@ managed memory, src/rakau_cuda.cu:434-527, and its README admits poor scaling). 
   sorted buckets and build the replicated tree from the globally sorted arrays. Per-rank sort work is N/P
   instead of N.
 * traversal: contiguous Morton ranges of critical nodes, cut by the previous evaluation's interaction counts
-  (rakau_b200.sharding); every rank broadcasts the output slice it owns.
+  (rakau_b200.sharding); the output slices are all-gathered (padded to the largest slice).
 """
 import numpy as np
 
@@ -180,13 +180,21 @@ class ShardedTree:
         self.tree.acc_pot(Q, theta, G=G, eps=eps, out=out, where=RK_DEVICE, crit_range=(c0, c1))
         info = self.tree.eval_info.asdict()
         if exchange:
-            # every rank owns one contiguous slice of the Morton-ordered result
-            # zero everything this rank does not own and sum: x + 0 is exact, one tuned collective per array
-            pb, pe = int(self.cut_particles[self.rank]), int(self.cut_particles[self.rank + 1])
-            for o in out:
-                o[:pb].zero_()
-                o[pe:].zero_()
-                self.dist.all_reduce(o)
+            # Every rank owns one contiguous slice of the Morton-ordered result: padded all-gather of the slices
+            # (one tuned NCCL collective per array, 7/8 of the array received per rank - an all-reduce of the
+            # zero-filled arrays moves twice that) + one copy per peer slice into place.
+            cp = [int(v) for v in self.cut_particles]
+            sizes = [cp[r + 1] - cp[r] for r in range(self.world)]
+            mx = max(sizes)
+            pb, pe = cp[self.rank], cp[self.rank + 1]
+            for j, o in enumerate(out):
+                pad = self._persistent('xp%d' % j, mx, o.dtype)
+                pad[:pe - pb] = o[pb:pe]
+                allb = self._persistent('xa%d' % j, mx * self.world, o.dtype)
+                self.dist.all_gather_into_tensor(allb, pad)
+                for r in range(self.world):
+                    if r != self.rank and sizes[r]:
+                        o[cp[r]:cp[r + 1]] = allb[r * mx:r * mx + sizes[r]]
         return info
 
     def rebalance(self, kernel_ms=None):
