@@ -87,6 +87,7 @@ def main():
         "workload": f"plummer_leapfrog_{a.nparts}_clipped_{n}_fp32_theta{a.theta}", "nparts": n, "steps": a.steps,
         "dt": a.dt, "eps": eps, "track_integrals": a.track,
         "ms_per_step": float(np.mean(ms_step)), "ms_per_step_min": float(np.min(ms_step)),
+        "ms_per_step_median": float(np.median(ms_step)), "ms_steps": [round(float(v), 3) for v in ms_step],
         "ms_kick_drift_rebuild": float(np.mean(ms_reb)),
         "ms_traverse_kernel": float(np.mean([e[3]["ms_kernel"] for e in evs])),
         "ms_rebuild_device": float(np.mean([e[4]["ms_total"] for e in evs])),
