@@ -121,13 +121,19 @@ RK_API int rk_tree_update_masses(rk_tree *t, const void *m, int where);
  * Distributed sample sort: every rank sorts its shard with the GLOBAL box (rk_tree_sort_shard; codes == NULL:
  * encode first), exchanges splitter buckets (NCCL all-to-all, done by the caller), sorts its bucket again with
  * the received codes, all-gathers the sorted buckets and builds the replicated tree from the globally sorted
- * arrays (rk_tree_build_presorted: topology + node properties only). All pointers are DEVICE pointers. */
+ * arrays (rk_tree_build_presorted: topology + node properties only). All pointers are DEVICE pointers.
+ * parts_ready_event: NULL, or a cudaEvent_t after which x, y, z, m and perm are valid - the topology is built from
+ * the codes alone, so the caller can gather the particle arrays on another stream underneath it. */
 RK_API int rk_tree_sort_shard(rk_tree *t, const void *x, const void *y, const void *z, const void *m,
                               const uint64_t *codes, size_t n, double box_size);
 RK_API int rk_tree_get_codes_device(rk_tree *t, uint64_t *out);
 RK_API int rk_tree_build_presorted(rk_tree *t, const void *x, const void *y, const void *z, const void *m,
                                    const uint64_t *codes, const uint32_t *perm, size_t n, double box_size,
-                                   size_t max_leaf_n, size_t ncrit, rk_build_info *info);
+                                   size_t max_leaf_n, size_t ncrit, void *parts_ready_event, rk_build_info *info);
+/* Copy-engine device-to-device copy on `stream` (cudaMemcpyAsync). dst may be PEER memory mapped into this process
+ * (CUDA IPC / symmetric memory): the multi-GPU output exchange pushes finished result slices into every peer's
+ * buffer with it while the next traversal launch occupies the SMs (an NCCL kernel would wait for them). */
+RK_API int rk_device_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 /* determine_box_size's final arithmetic (tree.hpp:1309-1312) for a global max |coordinate|. */
 RK_API double rk_deduce_box(int fp_bits, double absmax);
 /* Copy constructor / assignment (tree.hpp:1735-1743, 1785-1822): deep device-to-device copy of src into dst

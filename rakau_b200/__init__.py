@@ -32,7 +32,7 @@ SYMBOLS = [
     "rk_tree_update_masses", "rk_tree_clear", "rk_tree_nparts", "rk_tree_nnodes", "rk_tree_ncrit",
     "rk_tree_box_size", "rk_tree_get_parts", "rk_tree_get_codes", "rk_tree_get_perm", "rk_tree_get_nodes",
     "rk_tree_get_crit", "rk_tree_acc_pot", "rk_tree_acc_pot_range", "rk_tree_get_group_costs", "rk_tree_exact",
-    "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak",
+    "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak", "rk_device_copy_async",
     "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
     "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
 ]
@@ -110,6 +110,7 @@ def lib():
     L.rk_tree_group_costs_device.restype = vp
     L.rk_tree_group_costs_device.argtypes = [vp]
     L.rk_kernel_launch_count.restype = C.c_ulonglong
+    L.rk_device_copy_async.argtypes = [vp, vp, sz, vp]
     L.rk_measure_fp32_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.rk_plummer.argtypes = [i32, sz, sz, sz, dbl, dbl, i32, sz, i32, vp, vp, vp, vp]
     L.rk_plummer_leapfrog.argtypes = [i32, sz, dbl, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
@@ -117,7 +118,7 @@ def lib():
     L.rk_tree_get_perm_device.argtypes = [vp, i32, vp]
     L.rk_tree_sort_shard.argtypes = [vp, vp, vp, vp, vp, vp, sz, dbl]
     L.rk_tree_get_codes_device.argtypes = [vp, vp]
-    L.rk_tree_build_presorted.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, dbl, sz, sz, C.POINTER(BuildInfo)]
+    L.rk_tree_build_presorted.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, dbl, sz, sz, vp, C.POINTER(BuildInfo)]
     L.rk_tree_crit_begin_at.argtypes = [vp, vp, sz, vp]
     L.rk_deduce_box.restype = dbl
     L.rk_deduce_box.argtypes = [i32, dbl]
@@ -242,10 +243,13 @@ class Octree:
     def codes_device(self, out):
         self._check(self.L.rk_tree_get_codes_device(self.h, _ptr(out)))
 
-    def build_presorted(self, x, y, z, m, codes, perm, n, box_size, max_leaf_n=16, ncrit=128):
-        """Tree (topology + node properties) from globally sorted device arrays."""
+    def build_presorted(self, x, y, z, m, codes, perm, n, box_size, max_leaf_n=16, ncrit=128, parts_ready_event=None):
+        """Tree (topology + node properties) from globally sorted device arrays. parts_ready_event: cudaEvent_t
+        handle (int) after which x, y, z, m, perm are valid; the topology is built from the codes before it."""
         self._check(self.L.rk_tree_build_presorted(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(m), _ptr(codes), _ptr(perm),
-                                                   n, float(box_size), max_leaf_n, ncrit, C.byref(self.build_info)))
+                                                   n, float(box_size), max_leaf_n, ncrit,
+                                                   C.c_void_p(parts_ready_event) if parts_ready_event else None,
+                                                   C.byref(self.build_info)))
         return self.build_info
 
     def codes(self):
@@ -314,6 +318,13 @@ def device_count():
 def deduce_box(absmax, fp=32):
     """Box size the library deduces for a given max |coordinate| (tree.hpp:1309-1312)."""
     return lib().rk_deduce_box(fp, float(absmax))
+
+
+def device_copy_async(dst_ptr, src_ptr, nbytes, stream_ptr):
+    """Copy-engine D2D copy (dst may be mapped peer memory) on the given cudaStream_t handle."""
+    rc = lib().rk_device_copy_async(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nbytes, C.c_void_p(stream_ptr))
+    if rc:
+        raise RakauError(rc, "rk_device_copy_async failed")
 
 
 def kernel_launch_count():

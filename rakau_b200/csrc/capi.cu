@@ -298,9 +298,11 @@ public:
     }
     // Build the tree from globally sorted device arrays (SoA particles, codes, perm = original index of each
     // sorted particle): topology + node properties only.
+    // parts_ready: optional cudaEvent_t after which x, y, z, m and perm are valid. The topology needs only the codes,
+    // so a caller can all-gather the particle arrays on another stream while it is being built.
     void build_presorted(const void *x, const void *y, const void *z, const void *m, const uint64_t *codes_dev,
                          const uint32_t *perm_dev, size_t n, double box_size, size_t max_leaf_n, size_t ncrit,
-                         rk_build_info *info)
+                         void *parts_ready, rk_build_info *info)
     {
         use();
         clear();
@@ -317,18 +319,24 @@ public:
             reserve_particles(n);
             RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[0], m_stream));
             reset_flags();
-            launch_pack_absmax<F>(static_cast<const F *>(x), static_cast<const F *>(y), static_cast<const F *>(z),
-                                  static_cast<const F *>(m), m_b.psorted.p, n, reinterpret_cast<u64 *>(m_b.d_misc.p),
-                                  m_stream);
             RK_CUDA_CHECK(cudaMemcpyAsync(m_b.keys_a.p, codes_dev, n * sizeof(u64), cudaMemcpyDeviceToDevice, m_stream));
-            RK_CUDA_CHECK(cudaMemcpyAsync(m_b.perm.p, perm_dev, n * sizeof(u32), cudaMemcpyDeviceToDevice, m_stream));
-            RK_CUDA_CHECK(cudaMemcpyAsync(m_b.idx_a.p, perm_dev, n * sizeof(u32), cudaMemcpyDeviceToDevice, m_stream));
             m_b.codes = m_b.keys_a.p;
             m_b.last_perm = m_b.idx_a.p;
             for (int k = 1; k <= 3; ++k) {
                 RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[k], m_stream));
             }
-            finish_build(0, info);
+            finish_build(0, info, [&] {
+                if (parts_ready) {
+                    RK_CUDA_CHECK(cudaStreamWaitEvent(m_stream, static_cast<cudaEvent_t>(parts_ready), 0));
+                }
+                launch_pack_absmax<F>(static_cast<const F *>(x), static_cast<const F *>(y), static_cast<const F *>(z),
+                                      static_cast<const F *>(m), m_b.psorted.p, n,
+                                      reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
+                RK_CUDA_CHECK(
+                    cudaMemcpyAsync(m_b.perm.p, perm_dev, n * sizeof(u32), cudaMemcpyDeviceToDevice, m_stream));
+                RK_CUDA_CHECK(
+                    cudaMemcpyAsync(m_b.idx_a.p, perm_dev, n * sizeof(u32), cudaMemcpyDeviceToDevice, m_stream));
+            });
         } catch (...) {
             clear();
             throw;
@@ -1048,11 +1056,12 @@ private:
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[3], m_stream));
         m_pending_inv_box = inv_box;
         m_pending_check_encode = true;
-        finish_build(passes, info);
+        finish_build(passes, info, [] {});
     }
 
     // Topology + node properties on sorted codes / particles (events 0..3 already recorded).
-    void finish_build(int passes, rk_build_info *info)
+    template <typename Hook>
+    void finish_build(int passes, rk_build_info *info, Hook &&before_props)
     {
         const size_t n = m_b.n;
         if (info) {
@@ -1099,6 +1108,7 @@ private:
         topology_emit<F>(m_b, m_stream);
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[4], m_stream));
         // ---- node properties ----
+        before_props();
         node_properties<F>(m_b, m_mac, m_box, m_stream);
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
         RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_err.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
@@ -1381,9 +1391,11 @@ int rk_tree_get_codes_device(rk_tree *t, uint64_t *out)
 }
 int rk_tree_build_presorted(rk_tree *t, const void *x, const void *y, const void *z, const void *m,
                             const uint64_t *codes, const uint32_t *perm, size_t n, double box_size, size_t max_leaf_n,
-                            size_t ncrit, rk_build_info *info)
+                            size_t ncrit, void *parts_ready_event, rk_build_info *info)
 {
-    return guarded(t, [&]() { RK_WITH(t, T.build_presorted(x, y, z, m, codes, perm, n, box_size, max_leaf_n, ncrit, info)); });
+    return guarded(t, [&]() {
+        RK_WITH(t, T.build_presorted(x, y, z, m, codes, perm, n, box_size, max_leaf_n, ncrit, parts_ready_event, info));
+    });
 }
 double rk_deduce_box(int fp_bits, double absmax)
 {
@@ -1494,6 +1506,18 @@ const void *rk_tree_group_costs_device(rk_tree *t)
     return t->fp == 32 ? t->t32->group_costs_device() : t->t64->group_costs_device();
 }
 
+int rk_device_copy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (!bytes) {
+        return RK_OK;
+    }
+    if (!dst || !src) {
+        return RK_ERR_INVALID_ARGUMENT;
+    }
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) == cudaSuccess
+               ? RK_OK
+               : RK_ERR_RUNTIME;
+}
 unsigned long long rk_kernel_launch_count(void)
 {
     return __atomic_load_n(&rk::g_kernel_launches, __ATOMIC_RELAXED);

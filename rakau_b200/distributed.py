@@ -33,6 +33,8 @@ class ShardedTree:
         self.debug_barrier = bool(int(__import__('os').environ.get('RK_DEBUG_BARRIER', '0')))
         self.cuts = None
         self.cut_particles = None  # first particle of every rank's range
+        self._side = None  # stream of the particle all-gather that runs underneath the topology build
+        self._peer = None  # (capacity, buffers, per-buffer list of every rank's device pointer) or False
 
     # ---- build -------------------------------------------------------------------------------------------
     def build(self, x, y, z, m, first_index):
@@ -101,13 +103,26 @@ class ShardedTree:
             for r in range(self.world):
                 full[int(offs[r]):int(offs[r + 1])] = allb[r * mx:r * mx + sizes_l[r]]
             return full
-        fc, fx, fy, fz, fm, fi = (gather(k, t) for k, t in zip('cxyzmi', (bc, bx, by, bz, bm, bi)))
-        self._ev.append(('all_gather', self._rec()))
+        # The topology needs only the codes: gather them first, then gather the particle arrays on a side stream
+        # while rk_tree_build_presorted builds the topology on this one (it waits for `ready` before the node
+        # properties).
+        fc = gather('c', bc)
+        self._ev.append(('all_gather_codes', self._rec()))
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            fx, fy, fz, fm, fi = (gather(k, t) for k, t in zip('xyzmi', (bx, by, bz, bm, bi)))
+            ready = torch.cuda.Event()
+            ready.record(self._side)
         # 6. replicated topology + node properties
         self.n = n
         self.full_sorted = (fx, fy, fz, fm)  # keep alive
-        bi_ = self.tree.build_presorted(fx, fy, fz, fm, fc, fi, n, box, self.mln, self.ncrit)
-        self._ev.append(('topology_props', self._rec()))
+        bi_ = self.tree.build_presorted(fx, fy, fz, fm, fc, fi, n, box, self.mln, self.ncrit,
+                                        parts_ready_event=ready.cuda_event)
+        main.wait_stream(self._side)
+        self._ev.append(('topology_props_and_particle_gather', self._rec()))
         self.cut_particles = None
         return bi_
 
@@ -172,30 +187,97 @@ class ShardedTree:
         if self.cut_particles is None:
             self.cut_particles = self.tree.crit_begin_at(self.cuts).astype(np.int64)
 
-    def acc_pot(self, Q, theta, out, G=1.0, eps=0.0, exchange=True):
-        """Evaluate this rank's Morton range into `out` (device tensors of n elements, Morton order); with
-        exchange=True every rank ends with the full result."""
+    def _peer_outputs(self, nres):
+        """Result buffers in CUDA peer memory (torch symmetric memory: every rank maps every other rank's buffer),
+        allocated once for n particles. None if the platform cannot provide it (then NCCL does the exchange)."""
+        if self._peer is False:
+            return None
+        if self._peer is not None and self._peer[0] >= self.n and len(self._peer[1]) >= nres:
+            return self._peer
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            cap = int(self.n * 1.02) + 16
+            bufs, ptrs = [], []
+            for _ in range(max(nres, 3)):
+                t = symm_mem.empty(cap, dtype=self.dt, device=self.dev)
+                h = symm_mem.rendezvous(t, self.dist.group.WORLD)
+                bufs.append(t)
+                ptrs.append([int(p) for p in h.buffer_ptrs])
+            self._peer = (cap, bufs, ptrs)
+        except Exception as exc:  # noqa: BLE001 - no peer memory on this platform: use the collective path
+            self._peer = False
+            self._peer_error = repr(exc)
+            return None
+        return self._peer
+
+    def acc_pot(self, Q, theta, out=None, G=1.0, eps=0.0, exchange=True, chunks=(0.4, 0.7, 0.9)):
+        """Evaluate this rank's Morton range; with exchange=True every rank ends with the full result (Morton order).
+        Returns (info, outputs): outputs are `out` if given, else library-owned peer-memory buffers.
+
+        Peer-memory path (out=None): the range is evaluated in 4 launches (40/30/20/10 % of its critical nodes); as
+        soon as a launch has finished, its contiguous output slice is pushed into every peer's buffer with
+        copy-engine copies on a side stream (rk_device_copy_async) while the next launch occupies the SMs, so only the
+        last tenth of the exchange is exposed. An NCCL kernel could not overlap: the traversal's persistent CTAs
+        fill every SM. Collective path (out given, or no peer memory): padded all-gather of the owned slices."""
+        torch, dist = self.torch, self.dist
         self._ensure_cuts()
-        c0, c1 = self.cuts[self.rank], self.cuts[self.rank + 1]
-        self.tree.acc_pot(Q, theta, G=G, eps=eps, out=out, where=RK_DEVICE, crit_range=(c0, c1))
-        info = self.tree.eval_info.asdict()
-        if exchange:
-            # Every rank owns one contiguous slice of the Morton-ordered result: padded all-gather of the slices
-            # (one tuned NCCL collective per array, 7/8 of the array received per rank - an all-reduce of the
-            # zero-filled arrays moves twice that) + one copy per peer slice into place.
-            cp = [int(v) for v in self.cut_particles]
-            sizes = [cp[r + 1] - cp[r] for r in range(self.world)]
-            mx = max(sizes)
-            pb, pe = cp[self.rank], cp[self.rank + 1]
-            for j, o in enumerate(out):
-                pad = self._persistent('xp%d' % j, mx, o.dtype)
-                pad[:pe - pb] = o[pb:pe]
-                allb = self._persistent('xa%d' % j, mx * self.world, o.dtype)
-                self.dist.all_gather_into_tensor(allb, pad)
+        c0, c1 = int(self.cuts[self.rank]), int(self.cuts[self.rank + 1])
+        nres = {0: 3, 1: 1, 2: 4}[Q]
+        peer = self._peer_outputs(nres) if (out is None and exchange and self.world > 1) else None
+        if peer is None:
+            if out is None:
+                out = [self._persistent('o%d' % j, self.n, self.dt) for j in range(nres)]
+            self.tree.acc_pot(Q, theta, G=G, eps=eps, out=out, where=RK_DEVICE, crit_range=(c0, c1))
+            info = self.tree.eval_info.asdict()
+            if exchange and self.world > 1:
+                # padded all-gather of the slices (one tuned NCCL collective per array) + one copy per peer slice
+                cp = [int(v) for v in self.cut_particles]
+                sizes = [cp[r + 1] - cp[r] for r in range(self.world)]
+                mx = max(sizes)
+                pb, pe = cp[self.rank], cp[self.rank + 1]
+                for j, o in enumerate(out):
+                    pad = self._persistent('xp%d' % j, mx, o.dtype)
+                    pad[:pe - pb] = o[pb:pe]
+                    allb = self._persistent('xa%d' % j, mx * self.world, o.dtype)
+                    dist.all_gather_into_tensor(allb, pad)
+                    for r in range(self.world):
+                        if r != self.rank and sizes[r]:
+                            o[cp[r]:cp[r + 1]] = allb[r * mx:r * mx + sizes[r]]
+            return info, out
+        _, bufs, ptrs = peer
+        out = [b[:self.n] for b in bufs[:nres]]
+        from . import device_copy_async
+        nc = c1 - c0
+        ccuts = sorted({c0, c1, *[c0 + int(nc * f) for f in chunks]})
+        pcuts = [int(v) for v in self.tree.crit_begin_at(ccuts)]
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        side = self._side
+        side.wait_stream(main)
+        esz = out[0].element_size()
+        info = None
+        for k in range(len(ccuts) - 1):
+            self.tree.acc_pot(Q, theta, G=G, eps=eps, out=out, where=RK_DEVICE, crit_range=(ccuts[k], ccuts[k + 1]))
+            part = self.tree.eval_info.asdict()  # (the call returns after its launch has finished)
+            if info is None:
+                info = part
+            else:
+                for key in ("mac_tests", "accepted", "p2p_pairs", "self_pairs", "interactions", "n_groups",
+                            "kernel_launches", "ms_kernel", "ms_total"):
+                    info[key] += part[key]
+            b, e = pcuts[k], pcuts[k + 1]
+            if e > b:
                 for r in range(self.world):
-                    if r != self.rank and sizes[r]:
-                        o[cp[r]:cp[r + 1]] = allb[r * mx:r * mx + sizes[r]]
-        return info
+                    if r != self.rank:
+                        for j in range(nres):
+                            device_copy_async(ptrs[j][r] + b * esz, ptrs[j][self.rank] + b * esz, (e - b) * esz,
+                                              side.cuda_stream)
+        # every rank's pushes are ordered before its part of the barrier, so after it all slices have arrived
+        with torch.cuda.stream(side):
+            dist.barrier()
+        main.wait_stream(side)
+        return info, out
 
     def rebalance(self, kernel_ms=None):
         """Cost-weighted cuts from the last evaluation's per-group interaction counts. With kernel_ms (this rank's

@@ -21,11 +21,13 @@ sh = [torch.from_numpy(a).to(dev) for a in (x, y, z, m)]
 bi = st.build(*sh, first_index=first)
 for _rep in range(int(os.environ.get('REPS', '0'))):
     bi = st.build(*sh, first_index=first)
-out = [torch.zeros(N, dtype=torch.float32, device=dev) for _ in range(3)]
-st.acc_pot(0, 0.75, out)
+info, out = st.acc_pot(0, 0.75)  # peer-memory exchange (pipelined copy-engine pushes)
+out = [o.clone() for o in out]
+print(rank, "peer memory exchange:", st._peer is not False and st._peer is not None, flush=True)
 imb = st.rebalance()
 out2 = [torch.zeros(N, dtype=torch.float32, device=dev) for _ in range(3)]
-info = st.acc_pot(0, 0.75, out2)
+info2, _ = st.acc_pot(0, 0.75, out=out2)  # collective exchange (padded all-gather)
+assert info["interactions"] > 0 and info2["interactions"] > 0
 ok = True
 if rank == 0:
     fm, fx, fy, fz = rk.plummer(N, 0, N, chunk=chunk)
