@@ -34,6 +34,7 @@ class ShardedTree:
         self.cuts = None
         self.cut_particles = None  # first particle of every rank's range
         self._side = None  # stream of the particle all-gather that runs underneath the topology build
+        self._push = None  # per-peer copy streams of the output exchange
         self._peer = None  # (capacity, buffers, per-buffer list of every rank's device pointer) or False
 
     # ---- build -------------------------------------------------------------------------------------------
@@ -253,8 +254,12 @@ class ShardedTree:
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)
+        if self._push is None:
+            # one stream per peer: the copies to different peers run on different copy engines / NVLink ports
+            self._push = [torch.cuda.Stream(device=self.dev) for _ in range(self.world)]
         side = self._side
-        side.wait_stream(main)
+        for s in self._push:
+            s.wait_stream(main)
         esz = out[0].element_size()
         info = None
         for k in range(len(ccuts) - 1):
@@ -268,12 +273,14 @@ class ShardedTree:
                     info[key] += part[key]
             b, e = pcuts[k], pcuts[k + 1]
             if e > b:
-                for r in range(self.world):
-                    if r != self.rank:
-                        for j in range(nres):
-                            device_copy_async(ptrs[j][r] + b * esz, ptrs[j][self.rank] + b * esz, (e - b) * esz,
-                                              side.cuda_stream)
+                for d in range(1, self.world):
+                    r = (self.rank + d) % self.world  # staggered: at any time every rank receives from one peer
+                    for j in range(nres):
+                        device_copy_async(ptrs[j][r] + b * esz, ptrs[j][self.rank] + b * esz, (e - b) * esz,
+                                          self._push[r].cuda_stream)
         # every rank's pushes are ordered before its part of the barrier, so after it all slices have arrived
+        for s in self._push:
+            side.wait_stream(s)
         with torch.cuda.stream(side):
             dist.barrier()
         main.wait_stream(side)
