@@ -484,11 +484,26 @@ public:
     void crit_begin_at(const size_t *idx, size_t k, uint64_t *out)
     {
         use();
-        host_crit_begin();
         for (size_t i = 0; i < k; ++i) {
             if (idx[i] > m_b.n_crit) {
                 throw api_error(RK_ERR_INVALID_ARGUMENT, "critical node index out of range");
             }
+        }
+        if (k <= 64 && m_h_crit_begin.size() != m_b.n_crit + 1) {
+            // a handful of cut points (multi-GPU range cuts, every evaluation): fetch just those entries instead of
+            // mirroring the whole array (14 MB through pageable memory at 128 M particles)
+            u32 *h = reinterpret_cast<u32 *>(m_hpin + 16);
+            for (size_t i = 0; i < k; ++i) {
+                RK_CUDA_CHECK(cudaMemcpyAsync(h + i, m_b.crit_begin.p + idx[i], sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+            }
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+            for (size_t i = 0; i < k; ++i) {
+                out[i] = h[i];
+            }
+            return;
+        }
+        host_crit_begin();
+        for (size_t i = 0; i < k; ++i) {
             out[i] = m_h_crit_begin[idx[i]];
         }
     }
