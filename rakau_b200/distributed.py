@@ -17,20 +17,26 @@ from . import RK_DEVICE, RK_LAST_PERM, Octree, deduce_box, sharding
 
 
 class ShardedTree:
-    def __init__(self, dist, device, fp=32, mac="bh", max_leaf_n=16, ncrit=128, samples_per_rank=2048):
+    def __init__(self, dist, device, fp=32, mac="bh", max_leaf_n=16, ncrit=128, samples_per_rank=2048,
+                 octree_factory=None):
+        """octree_factory(fp=, mac=, device=): the per-rank tree backend, rakau_b200.Octree unless given. The CPU
+        tests (tests/test_sharding_gloo.py) run this class over gloo with a numpy stand-in for the backend, so the
+        orchestration below - splitters, bucket exchange, gathers, range cuts, output exchange - is exercised
+        without a GPU; the product always uses the CUDA library."""
         import torch
         self.torch, self.dist, self.dev = torch, dist, device
+        self.cuda = device.type == "cuda"
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.fp, self.mln, self.ncrit = fp, max_leaf_n, ncrit
         self.dt = torch.float32 if fp == 32 else torch.float64
-        idx = device.index
-        self.local, self.bucket, self.tree = (Octree(fp=fp, mac=mac, device=idx) for _ in range(3))
-        s = torch.cuda.current_stream().cuda_stream
-        for t in (self.local, self.bucket, self.tree):
-            t.set_stream(s)
+        make = octree_factory or Octree
+        self.local, self.bucket, self.tree = (make(fp=fp, mac=mac, device=device.index) for _ in range(3))
+        if self.cuda:
+            s = torch.cuda.current_stream().cuda_stream
+            for t in (self.local, self.bucket, self.tree):
+                t.set_stream(s)
         self.nsamp = samples_per_rank
         self._bufs = {}
-        self.debug_barrier = bool(int(__import__('os').environ.get('RK_DEBUG_BARRIER', '0')))
         self.cuts = None
         self.cut_particles = None  # first particle of every rank's range
         self._side = None  # stream of the particle all-gather that runs underneath the topology build
@@ -80,9 +86,6 @@ class ShardedTree:
         bc, bx, by, bz, bm, blp = self._sorted_arrays(self.bucket, n_b)
         bi = bi[blp.long()]
         self._ev.append(('bucket_sort', self._rec()))
-        if self.debug_barrier:
-            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-            self._ev.append(('skew_before_gather', self._rec()))
         # 5. uneven all-gather of the sorted buckets straight into the full arrays (grouped NCCL send/recv)
         sizes = torch.empty(self.world, dtype=torch.int64, device=self.dev)
         dist.all_gather_into_tensor(sizes, torch.tensor([n_b], dtype=torch.int64, device=self.dev))
@@ -109,31 +112,40 @@ class ShardedTree:
         # properties).
         fc = gather('c', bc)
         self._ev.append(('all_gather_codes', self._rec()))
-        main = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.dev)
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
+        ready = None
+        if self.cuda:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                fx, fy, fz, fm, fi = (gather(k, t) for k, t in zip('xyzmi', (bx, by, bz, bm, bi)))
+                ready = torch.cuda.Event()
+                ready.record(self._side)
+        else:
             fx, fy, fz, fm, fi = (gather(k, t) for k, t in zip('xyzmi', (bx, by, bz, bm, bi)))
-            ready = torch.cuda.Event()
-            ready.record(self._side)
         # 6. replicated topology + node properties
         self.n = n
         self.full_sorted = (fx, fy, fz, fm)  # keep alive
         bi_ = self.tree.build_presorted(fx, fy, fz, fm, fc, fi, n, box, self.mln, self.ncrit,
-                                        parts_ready_event=ready.cuda_event)
-        main.wait_stream(self._side)
+                                        parts_ready_event=ready.cuda_event if ready is not None else None)
+        if self.cuda:
+            main.wait_stream(self._side)
         self._ev.append(('topology_props_and_particle_gather', self._rec()))
         self.cut_particles = None
         return bi_
 
     def _rec(self):
+        if not self.cuda:
+            return None
         e = self.torch.cuda.Event(enable_timing=True)
         e.record()
         return e
 
     def phase_ms(self):
         """CUDA-event time of the build phases of the last build() on this rank."""
+        if not self.cuda:
+            return {}
         self.torch.cuda.synchronize()
         return {self._ev[i][0]: self._ev[i - 1][1].elapsed_time(self._ev[i][1]) for i in range(1, len(self._ev))}
 
@@ -224,7 +236,7 @@ class ShardedTree:
         self._ensure_cuts()
         c0, c1 = int(self.cuts[self.rank]), int(self.cuts[self.rank + 1])
         nres = {0: 3, 1: 1, 2: 4}[Q]
-        peer = self._peer_outputs(nres) if (out is None and exchange and self.world > 1) else None
+        peer = self._peer_outputs(nres) if (out is None and exchange and self.world > 1 and self.cuda) else None
         if peer is None:
             if out is None:
                 out = [self._persistent('o%d' % j, self.n, self.dt) for j in range(nres)]

@@ -58,3 +58,70 @@ def test_cut_helpers_edge_cases():
     assert c == [0, 25, 50, 75, 100]
     c = sharding.cuts_by_particles(np.arange(0, 1000, 10), 1000, 4)
     assert c == [0, 25, 50, 75, 100]
+
+
+def _sharded_worker(rank, world, port, q):
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cpu_backend import CpuOctree, morton_codes
+    from rakau_b200 import deduce_box
+    from rakau_b200.distributed import ShardedTree
+    rng = np.random.default_rng(7)  # the full particle set, identical on every rank
+    N = 50_000
+    full = [rng.normal(size=N).astype(np.float32) for _ in range(3)] + [rng.uniform(0.1, 1.9, N).astype(np.float32)]
+    full[0][:200] = full[0][200:400]  # duplicated coordinates => equal Morton codes: the stable order must survive
+    full[1][:200] = full[1][200:400]
+    full[2][:200] = full[2][200:400]
+    per = 30_000  # uneven shards: 30000 + 20000
+    first = rank * per
+    cnt = min(N, first + per) - first
+    shard = [torch.from_numpy(a[first:first + cnt].copy()) for a in full]
+    st = ShardedTree(dist, torch.device("cpu"), fp=32, ncrit=96, samples_per_rank=64, octree_factory=CpuOctree)
+    st.build(*shard, first_index=first)
+    # reference: one stable sort of everything
+    box = deduce_box(float(max(np.abs(a).max() for a in full[:3])), 32)
+    codes = morton_codes(full[0], full[1], full[2], box)
+    p = np.argsort(codes, kind="stable")
+    ok_build = bool((st.tree._codes == codes[p]).all()) and bool((st.tree._perm == p).all())
+    ok_build &= all(bool((a == b[p]).all()) for a, b in zip(st.tree._parts, full))
+    # evaluation 1 (cuts by particle count), rebalance, evaluation 2 (cuts by cost): every rank ends with everything
+    info1, out1 = st.acc_pot(0, 0.75)
+    cuts1 = list(st.cuts)
+    out1 = [o.clone() for o in out1]
+    imb = st.rebalance(kernel_ms=1.0 + rank)
+    cuts2 = list(st.cuts)
+    mine = [torch.full((N,), float("nan")) for _ in range(3)]
+    info2, out2 = st.acc_pot(0, 0.75, out=mine)
+    sorted_parts = [a[p] for a in full]
+    ok_eval = all(bool((o.numpy()[:N] == CpuOctree.expected(sorted_parts, j)).all()) for j, o in enumerate(out1))
+    ok_eval &= all(bool((o.numpy() == CpuOctree.expected(sorted_parts, j)).all()) for j, o in enumerate(out2))
+    tot = torch.tensor([info1["interactions"], info2["interactions"]], dtype=torch.int64)
+    dist.all_reduce(tot)
+    q.put((rank, ok_build, ok_eval, cuts1, cuts2, imb, tot.tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharded_tree_orchestration_two_ranks():
+    """rakau_b200.distributed.ShardedTree over gloo with the numpy backend of tests/cpu_backend.py: the distributed
+    sample sort reproduces the single stable sort (codes, permutation, particle order, ties included), both
+    ranks end with the complete result of both evaluations, and they agree on the range cuts."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, ba, ea, c1a, c2a, ia, ta), (_, bb, eb, c1b, c2b, ib, tb) = res
+    assert ba and bb and ea and eb
+    assert c1a == c1b and c2a == c2b and c1a[0] == 0 and c1a[-1] == c2a[-1]
+    assert c2a != c1a  # the time-weighted rebalance moved the cut (rank 1 reported a slower kernel)
+    assert ta == tb and ta[0] == ta[1]  # every group evaluated exactly once per evaluation
+    assert ia == ib
