@@ -107,7 +107,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline (the ONLY users of oracle/ in this file)
 # ----------------------------------------------------------------------------------------------------------
-def cpu_reference_run(args, nparts, steps, warmup, target_seconds):
+def cpu_reference_run(args, nparts, steps, warmup, target_seconds, chunk=0):
     """Times the reference's CPU implementation of the path on the host cores.
 
     Preferred: oracle/_ref (the UNMODIFIED reference header compiled against dependency stand-ins, SIMD + rsqrt
@@ -118,7 +118,7 @@ def cpu_reference_run(args, nparts, steps, warmup, target_seconds):
     import oracle  # noqa: test infrastructure, allowed here only
     import rakau_b200 as rk
     cores = os.cpu_count() or 1
-    m, x, y, z = rk.plummer(nparts)
+    m, x, y, z = rk.plummer(nparts, 0, nparts, chunk=chunk) if chunk else rk.plummer(nparts)
     t0 = time.time()
     otree = oracle.OracleTree(x, y, z, m, max_leaf_n=args.max_leaf_n, ncrit=args.ncrit)
     t_obuild = time.time() - t0
@@ -193,8 +193,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nparts = args.nparts or 4_000_000  # the reference arm always runs the CPU-runnable config
-    r = cpu_reference_run(args, nparts, args.steps, args.warmup, 150.0)
+    # the arm's own workload: 4 M particles at N = 1, the 128 M strong-scaling workload (chunked generator) at N > 1,
+    # where the number of timed steps is bounded by wall clock (one evaluation takes ~15-20 s on 16 host cores)
+    big = args.gpus > 1 and not args.nparts
+    nparts = args.nparts or (128_000_000 if big else 4_000_000)
+    r = cpu_reference_run(args, nparts, args.steps, min(args.warmup, 1) if big else args.warmup, 60.0 if big else 150.0,
+                          chunk=(1 << 20) if args.gpus > 1 else 0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Ginteractions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
