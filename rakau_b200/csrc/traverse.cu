@@ -212,12 +212,6 @@ __device__ __forceinline__ u64 pk2(float lo, float hi)
     return d;
 }
 __device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 add2(u64 a, u64 b)
-{
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 __device__ __forceinline__ u64 sub2(u64 a, u64 b)
 {
     u64 d;
