@@ -49,7 +49,10 @@ class ShardedTree:
         torch, dist = self.torch, self.dist
         n_loc = x.numel()
         self._ev = [('start', self._rec())]
-        amax = torch.stack([x.abs().max(), y.abs().max(), z.abs().max()]).max().double().reshape(1)
+        if n_loc:
+            amax = torch.stack([x.abs().max(), y.abs().max(), z.abs().max()]).max().double().reshape(1)
+        else:  # a rank may hold no particles at all
+            amax = torch.zeros(1, dtype=torch.float64, device=self.dev)
         dist.all_reduce(amax, op=dist.ReduceOp.MAX)
         box = deduce_box(float(amax.item()), self.fp)
         # 1. local sort of the shard

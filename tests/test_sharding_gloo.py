@@ -75,9 +75,10 @@ def _sharded_worker(rank, world, port, q):
     full[0][:200] = full[0][200:400]  # duplicated coordinates => equal Morton codes: the stable order must survive
     full[1][:200] = full[1][200:400]
     full[2][:200] = full[2][200:400]
-    per = 30_000  # uneven shards: 30000 + 20000
-    first = rank * per
-    cnt = min(N, first + per) - first
+    if world == 2:
+        first, cnt = (0, 30_000) if rank == 0 else (30_000, N - 30_000)  # uneven shards
+    else:  # three ranks, the middle one holds nothing
+        first, cnt = [(0, 35_000), (35_000, 0), (35_000, N - 35_000)][rank]
     shard = [torch.from_numpy(a[first:first + cnt].copy()) for a in full]
     st = ShardedTree(dist, torch.device("cpu"), fp=32, ncrit=96, samples_per_rank=64, octree_factory=CpuOctree)
     st.build(*shard, first_index=first)
@@ -104,11 +105,15 @@ def _sharded_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_sharded_tree_orchestration_two_ranks():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_tree_orchestration(world):
     """rakau_b200.distributed.ShardedTree over gloo with the numpy backend of tests/cpu_backend.py: the distributed
-    sample sort reproduces the single stable sort (codes, permutation, particle order, ties included), both
-    ranks end with the complete result of both evaluations, and they agree on the range cuts."""
-    world = 2
+    sample sort reproduces the single stable sort (codes, permutation, particle order, ties included), all
+    ranks end with the complete result of both evaluations, and they agree on the range cuts. world = 3: one
+    rank starts with an empty shard."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + os.getpid() % 2000
@@ -119,9 +124,10 @@ def test_sharded_tree_orchestration_two_ranks():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, ba, ea, c1a, c2a, ia, ta), (_, bb, eb, c1b, c2b, ib, tb) = res
-    assert ba and bb and ea and eb
-    assert c1a == c1b and c2a == c2b and c1a[0] == 0 and c1a[-1] == c2a[-1]
-    assert c2a != c1a  # the time-weighted rebalance moved the cut (rank 1 reported a slower kernel)
-    assert ta == tb and ta[0] == ta[1]  # every group evaluated exactly once per evaluation
-    assert ia == ib
+    _, ba, ea, c1a, c2a, ia, ta = res[0]
+    for _, bb, eb, c1b, c2b, ib, tb in res:
+        assert bb and eb
+        assert c1a == c1b and c2a == c2b and ia == ib and ta == tb
+    assert len(c1a) == world + 1 and c1a[0] == 0 and c1a[-1] == c2a[-1]
+    assert c2a != c1a  # the time-weighted rebalance moved the cuts (higher ranks reported slower kernels)
+    assert ta[0] == ta[1]  # every group evaluated exactly once per evaluation
