@@ -213,6 +213,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def strong_scaling_base(nparts, ms_per_step):
+    """The same workload on ONE GPU, from the committed profile (the N = 1 line of this script measures the 4 M
+    headline workload, not this one): lets a reader form the strong-scaling speed-up on equal work."""
+    try:
+        path = os.path.join(ROOT, "profiles", "r01_bench_1gpu_128M_v7.json")
+        d = json.loads(open(path).read().strip().splitlines()[-1])
+        if int(d["config"]["nparts"]) != int(nparts):
+            return None
+        return {"n_gpus": 1, "ms_per_step": d["ms_per_step"], "value": d["value"], "source": os.path.relpath(path, ROOT),
+                "speedup_vs_1gpu": d["ms_per_step"] / ms_per_step}
+    except Exception:  # informational only
+        return None
+
+
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
@@ -409,6 +423,7 @@ def run_ours(args):
         line["ms_traverse_kernel_per_rank"] = [float(k.item()) for k in kall]
         line["build_note"] = ("ms_build = distributed sample sort (local sort, all-to-all, bucket sort, all-gather) + "
                               "replicated topology/properties; build_phases_ms covers the replicated part only")
+        line["strong_scaling_base"] = strong_scaling_base(nparts, ms_per_step)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             r = cpu_reference_run(args, nparts, 4, 1, args.cpu_seconds)
