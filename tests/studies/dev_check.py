@@ -1,7 +1,7 @@
 """Developer smoke: GPU build + traversal vs the oracle at a few sizes, with timings. Run under gpurun."""
 import sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle
 from oracle import OracleTree
 import rakau_b200 as rk

@@ -2,12 +2,12 @@
 import sys, time, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle
+import rakau_b200 as _rk
 import rakau_b200 as rk
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 cfgs = [(16, 128), (16, 64), (16, 256), (32, 128), (8, 64), (32, 256), (64, 256)]
-t0 = time.time(); m, x, y, z = oracle.plummer(N); print("gen", time.time() - t0, flush=True)
+t0 = time.time(); m, x, y, z = _rk.plummer(N); print("gen", time.time() - t0, flush=True)
 g = rk.Octree()
 for mln, nc in cfgs:
     for it in range(3):
