@@ -178,6 +178,7 @@ struct build_arrays {
     dbuf<u32> crit_node;  // BFS index of each critical node
     dbuf<u32> crit_begin; // n_crit + 1 (crit_begin[n_crit] = n)
     dbuf<double> chunksum; // 4 doubles per chunk of PROPS_CHUNK particles
+    dbuf<double> nodesum;  // 4 doubles per node (experimental bottom-up node properties only)
     level_table levels;
     dbuf<dev_error> d_err;
     dbuf<u32> d_misc; // [0..1] abs-max bits (u64), [2] max group size
