@@ -628,6 +628,7 @@ public:
         p.tmax = tmax ? tmax : 32;
         p.err = m_work.p + 1;
         p.out_offset = 0;
+        p.window = trav_window(p.tmax, m_max_group);
         for (int j = 0; j < nres; ++j) {
             if (where == RK_DEVICE) {
                 p.out[j] = static_cast<F *>(out[j]);
@@ -891,6 +892,7 @@ public:
         p.tmax = tmax ? tmax : 32;
         p.err = m_work.p + 1;
         p.out_offset = static_cast<u32>(first);
+        p.window = trav_window(p.tmax, max_group);
         const int nres = Q == 0 ? 3 : (Q == 1 ? 1 : 4);
         const size_t cnt_out = n - first;
         for (int j = 0; j < nres; ++j) {

@@ -249,7 +249,10 @@ struct trav_params {
     u32 tmax;        // targets staged in shared memory per warp
     u32 *err;        // stack overflow flag
     u32 out_offset;  // subtracted from the particle index when writing (external-tree drop-in)
+    u32 window;      // two-phase walk: particles per run of sibling groups (trav_window()); 0 = one group per unit
 };
+// Window of the two-phase walk for groups of at most max_group targets (0 when a group exceeds the staging area).
+u32 trav_window(u32 tmax, size_t max_group);
 template <typename F>
 void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cudaStream_t st);
 // FFMA-bound microbenchmark on the current device: returns the flop count, *ms the CUDA-event time.

@@ -82,6 +82,7 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #define RK_STACK 512
 #endif
 constexpr int STACK_CAP = RK_STACK;   // (first child, count) entries per warp (<= 32 pushes per step, depth <= 21)
+constexpr int FRONT_CAP = 128;        // frontier nodes of a run of sibling groups (two-phase walk, see traverse_kernel)
 constexpr u32 FULL = 0xffffffffu;
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
@@ -367,9 +368,39 @@ __host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax, u32 LCAP)
 {
     // ring + staged targets + accumulators + stack + queues
     return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(acc_entries(tmax)) * sizeof(vec4<F>)
-           + size_t(STACK_CAP) * 4 + 32 * 4 /*nodebuf*/ + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
+           + size_t(STACK_CAP) * 4 + size_t(FRONT_CAP) * 4 + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
 }
 
+// First index j in [a, b) with arr[j] >= x, else b; the 32 lanes probe 32 positions per round (monotone array).
+__device__ __forceinline__ u32 warp_lower_bound(const u32 *__restrict__ arr, u32 a, u32 b, u32 x, int lane)
+{
+    u32 lo = a, n = b - a; // the answer lies in [lo, lo + n]
+    while (n > 0u) {
+        const u32 step = (n + 32u) / 33u, idx = lo + (static_cast<u32>(lane) + 1u) * step - 1u;
+        const bool less = idx < lo + n && arr[idx] < x;
+        const u32 c = __popc(__ballot_sync(FULL, less)); // probes below x form a prefix of the lanes
+        const u32 nlo = lo + c * step, nhi = lo + (c + 1u) * step - 1u;
+        n = (nhi < lo + n ? nhi : lo + n) - nlo;
+        lo = nlo;
+    }
+    return lo;
+}
+
+// Work units. p.window == 0: one critical node (group) per unit, walked from the root (the round-1 scheme).
+// p.window == W > 0: TWO-PHASE walk of a RUN of sibling groups - the critical nodes whose first particle lies in
+// one W-aligned window of the Morton-sorted particles (~7 groups, W .. W + tmax - 1 targets):
+//   phase 1, once per run: walk from the root with the bounding box of ALL the run's targets. A node whose MAC
+//     holds for the whole box is accepted by every group of the run (tree.hpp:2666-2672 holds for each target), a
+//     node whose MAC fails even for the farthest corner of the box is rejected by every group (each of them has a
+//     failing target): those two classes - and the ancestors of the whole run - are resolved ONCE, their sources
+//     are evaluated against all the run's targets at full lane utilisation, and the partial sums are parked in the
+//     output arrays. Every other node (undecided by the box, or overlapping the run) goes to the run's FRONTIER;
+//   phase 2, per group: the reference's group walk with the exact group MAC, started from the frontier nodes
+//     instead of the root; the group's sums are added to the parked partial sums.
+// A group never sees a descendant of a node it accepts, and every node test has the reference's outcome, so the
+// per-group decisions and the interaction counts are exactly those of tree_acc_pot (tests T1); only the order of
+// the additions differs. On the 4M Plummer tree this removes 47 % of the node visits and 43 % of the interactions
+// come from phase 1 (tests/studies/two_phase_walk_study.py).
 template <typename F, int Q, int MAC, int BATCH_>
 __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const trav_params<F> p)
 {
@@ -381,24 +412,51 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
     vec4<F> *tgt = ring + LCAP;
     vec4<F> *acc = tgt + p.tmax;
     u32 *stack = reinterpret_cast<u32 *>(acc + acc_entries(p.tmax));
-    const u32 rr_cap = acc_entries(p.tmax) / 32u; // accumulator slots per lane
-    u32 *nodebuf = stack + STACK_CAP;
-    u32 *lq_incl = nodebuf + 32;
+    const u32 rr_cap = acc_entries(p.tmax) / 32u;              // accumulator slots per lane (one group)
+    const u32 rr_cap1 = (p.tmax + acc_entries(p.tmax)) / 32u; // phase 1: the staged-target area holds accumulators too
+    u32 *front = stack + STACK_CAP;
+    u32 *lq_incl = front + FRONT_CAP;
     u32 *lq_base = lq_incl + 32;
     const u32 ltm = lanemask_lt();
     const F eps2 = p.eps2;
+    const u32 W = p.window;
+    const u32 win0 = W ? p.crit_begin[p.c0] / W : 0u;
+    const u32 n_units = W ? (p.crit_begin[p.c1] - 1u) / W - win0 + 1u : p.c1 - p.c0;
 
     for (;;) {
-        u32 g = 0;
+        u32 u = 0;
         if (lane == 0) {
-            g = atomicAdd(p.work_counter, 1u);
+            u = atomicAdd(p.work_counter, 1u);
         }
-        g = __shfl_sync(FULL, g, 0) + p.c0;
-        if (g >= p.c1) {
+        u = __shfl_sync(FULL, u, 0);
+        if (u >= n_units) {
             break;
         }
-        const u32 gnode = p.crit_node[g], gb = p.crit_begin[g], ge = p.crit_begin[g + 1], T = ge - gb;
-        const bool staged = T <= p.tmax;
+        u32 j0 = p.c0 + u, j1 = j0 + 1u;
+        if (W) {
+            const u32 lo = (win0 + u) * W;
+            j0 = warp_lower_bound(p.crit_begin, p.c0, p.c1, lo, lane);
+            const u32 lim = p.c1 - j0 < W ? p.c1 : j0 + W; // a window holds at most W groups
+            j1 = warp_lower_bound(p.crit_begin, j0, lim, lo + W, lane);
+            if (j0 == j1) {
+                continue;
+            }
+        }
+        const u32 ng = j1 - j0;
+        // stage 0 = phase 1 of the run (skipped for a single group: the walk then starts at the root), stages 1..ng =
+        // its groups
+        u32 fcount = 1u;                       // frontier size; {root} unless phase 1 fills it
+        u32 n_mac1 = 0, n_acc1 = 0, n_p2p1 = 0; // phase-1 tests / accepted nodes / leaf particles: shared by all groups
+        bool have_partial = false;
+        if (lane == 0) {
+            front[0] = 0u;
+        }
+        for (u32 s = ng > 1u ? 0u : 1u; s <= ng; ++s) {
+        const bool ph1 = s == 0u;
+        const u32 g = ph1 ? j0 : j0 + s - 1u;
+        const u32 gnode = ph1 ? 0xffffffffu : p.crit_node[g], gb = p.crit_begin[g], ge = p.crit_begin[ph1 ? j1 : g + 1u],
+                  T = ge - gb;
+        const bool staged = !ph1 && T <= p.tmax;
         const vec4<F> *gsrc = p.parts + gb;
         __syncwarp();
         // Stage the targets (MAC test + self interactions) and compute the group's bounding box.
@@ -416,14 +474,14 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 if (staged) {
                     tgt[i] = v;
                 }
-                if (i < 256u) {
+                if (i < 256u && !ph1) {
                     // keys = (order-preserving bits of the functional, 8 low bits replaced by the target index)
                     const float fx = static_cast<float>(v.x), fy = static_cast<float>(v.y), fz = static_cast<float>(v.z);
-                    const float s[4] = {(fx + fy) + fz, (fx + fy) - fz, (fx - fy) + fz, (fx - fy) - fz};
+                    const float sk[4] = {(fx + fy) + fz, (fx + fy) - fz, (fx - fy) + fz, (fx - fy) - fz};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const u32 b = __float_as_uint(s[q]), u = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
-                        const u32 k1 = (u & 0xffffff00u) | i, k2 = (~u & 0xffffff00u) | i;
+                        const u32 b = __float_as_uint(sk[q]), uu = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+                        const u32 k1 = (uu & 0xffffff00u) | i, k2 = (~uu & 0xffffff00u) | i;
                         kmax[q] = k1 > kmax[q] ? k1 : kmax[q];
                         kmin[q] = k2 > kmin[q] ? k2 : kmin[q];
                     }
@@ -466,8 +524,10 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
         // repeating the traversal (the MAC always spans the whole group, as in the reference).
         const vec4<F> *tpos = staged ? tgt : gsrc;
         const F bmid[3] = {(blo[0] + bhi[0]) * F(0.5), (blo[1] + bhi[1]) * F(0.5), (blo[2] + bhi[2]) * F(0.5)};
-        for (u32 t0 = 0; t0 < T; t0 += 32u * rr_cap) {
-            const u32 tc = (T - t0 < 32u * rr_cap) ? (T - t0) : 32u * rr_cap;
+        const u32 cap = ph1 ? rr_cap1 : rr_cap;
+        vec4<F> *acc_lane = (ph1 ? tgt : acc) + lane; // phase 1 reads its targets from global memory (L1)
+        for (u32 t0 = 0; t0 < T; t0 += 32u * cap) {
+            const u32 tc = (T - t0 < 32u * cap) ? (T - t0) : 32u * cap;
             // Slice the warp: P lanes per slice, S = 32/P slices, rr target slots per lane; minimise rr * P >= tc.
             // Cost of a choice = slots + half a slot per lane when rr is odd: the fp32 loop evaluates two slots per
             // packed instruction, an unpaired last slot runs the scalar loop at twice the issue cost.
@@ -476,22 +536,26 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
 #pragma unroll
             for (u32 l = 4u; l >= 2u; --l) {
                 const u32 r = (tc + (1u << l) - 1u) >> l, cost = (2u * r + (r & 1u)) << l;
-                if (r <= rr_cap && cost < best) {
+                if (r <= cap && cost < best) {
                     best = cost;
                     lp = l;
                     rr = r;
                 }
             }
             const u32 P = 1u << lp, sl = static_cast<u32>(lane) >> lp, tl = static_cast<u32>(lane) & (P - 1u);
-            vec4<F> *acc_lane = acc + lane;
             for (u32 k = 0; k < rr; ++k) {
                 acc_lane[32u * k] = make_vec4<F>(F(0), F(0), F(0), F(0));
             }
 
-            u32 sp = 1, lhead = 0, lcount = 0, lq_total = 0, lq_done = 0;
-            bool done = false, overflow = false;
-            if (lane == 0) {
-                stack[0] = 0u; // root: first = 0, count = 1
+            // phase 1 starts at the root; a group starts at the run's frontier (the root when there was no phase 1)
+            u32 sp = ph1 ? 1u : 0u, fpos = 0u, lhead = 0, lcount = 0, lq_total = 0, lq_done = 0;
+            const u32 fend = ph1 ? 0u : fcount;
+            bool done = false, overflow = false, fover = false;
+            if (ph1) {
+                fcount = 0u;
+                if (lane == 0) {
+                    stack[0] = 0u; // root: first = 0, count = 1
+                }
             }
             __syncwarp();
 
@@ -505,9 +569,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                         for (u32 f = lq_done + lane; f < lq_done + chunk; f += 32) {
                             int lo = 0;
 #pragma unroll
-                            for (int s = 16; s > 0; s >>= 1) {
-                                if (lq_incl[lo + s - 1] <= f) {
-                                    lo += s;
+                            for (int st = 16; st > 0; st >>= 1) {
+                                if (lq_incl[lo + st - 1] <= f) {
+                                    lo += st;
                                 }
                             }
                             const u32 pidx = lq_base[lo] + f;
@@ -518,22 +582,28 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                         lq_done += chunk;
                         continue;
                     }
-                    if (sp == 0) {
+                    bool have = false;
+                    u32 k = 0;
+                    if (sp != 0u) {
+                        // ---- pop up to 4 (first child, count) entries: lane -> entry lane>>3, child lane&7 ----
+                        // (an internal node of the 4M Plummer tree has 7.1 children on average, so this keeps
+                        // ~7/8 of the lanes busy without the prefix scan / expansion buffer an exact 32-node pop needs)
+                        const u32 eidx = static_cast<u32>(lane) >> 3, cidx = static_cast<u32>(lane) & 7u;
+                        if (eidx < sp) {
+                            const u32 e = stack[sp - 1u - eidx];
+                            have = cidx <= (e & 7u);
+                            k = (e >> 3) + cidx;
+                        }
+                        sp -= sp < 4u ? sp : 4u;
+                    } else if (fpos < fend) {
+                        // ---- the stack is empty: the next 32 frontier nodes ----
+                        have = fpos + static_cast<u32>(lane) < fend;
+                        k = front[have ? fpos + static_cast<u32>(lane) : 0u];
+                        fpos += 32u;
+                    } else {
                         done = true;
                         break;
                     }
-                    // ---- pop up to 4 (first child, count) entries: lane -> entry lane>>3, child lane&7 ----
-                    // (an internal node of the 4M Plummer tree has 7.1 children on average, so this keeps
-                    // ~7/8 of the lanes busy without the prefix scan / expansion buffer an exact 32-node pop needs)
-                    const u32 eidx = static_cast<u32>(lane) >> 3, cidx = static_cast<u32>(lane) & 7u;
-                    bool have = false;
-                    u32 k = 0;
-                    if (eidx < sp) {
-                        const u32 e = stack[sp - 1u - eidx];
-                        have = cidx <= (e & 7u);
-                        k = (e >> 3) + cidx;
-                    }
-                    sp -= sp < 4u ? sp : 4u;
                     __syncwarp();
 
                     // ---- one node per lane: classify ----
@@ -545,8 +615,11 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     }
                     const u32 nch = nb.w & 0xffu, level = nb.w >> 8;
                     const bool is_self = have && k == gnode;
+                    // (phase 1: [gb, ge) is the whole run, so this is "ancestor of every group")
                     const bool is_anc = have && !is_self && nb.x <= gb && ge <= nb.y;
-                    const bool test = have && !is_self && !is_anc;
+                    // phase 1: a node overlapping the run is some group's own node, ancestor or descendant
+                    bool fr = ph1 && have && !is_anc && nb.x < ge && nb.y > gb;
+                    const bool test = have && !is_self && !is_anc && !fr;
                     F mac_lh = F(0);
                     if (test) {
                         if (MAC == 0) {
@@ -564,6 +637,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     // which is (nearly always) its nearest target: if it fails, the node is rejected, exactly as in
                     // the reference. On the 4M Plummer tree 80 % of the tests end at (1), 18 % at (2); only the
                     // remaining 2 % run the exact loop over all the targets.
+                    // Phase 1 (box of a whole run): (2') if the MAC fails even at the farthest corner of the box it
+                    // fails for every target, so every group rejects the node; anything else joins the frontier.
                     bool sure_acc = false, sure_rej = false;
                     if (test) {
                         F dmin2 = F(0);
@@ -575,17 +650,28 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                         }
                         sure_acc = mac_lh < dmin2 * (F(1) - F(9.5367431640625e-07));
                         if (!sure_acc) {
-                            const u32 q = (c[1] < bmid[1] ? 2u : 0u) + (c[2] < bmid[2] ? 1u : 0u);
-                            const u32 ci = ((c[0] < bmid[0] ? cand_neg : cand_pos) >> (8u * q)) & 0xffu;
-                            const vec4<F> t = tpos[ci];
-                            const F dx = rn_sub(na.x, t.x), dy = rn_sub(na.y, t.y), dz = rn_sub(na.z, t.z);
-                            F d2 = rn_mul(dx, dx);
-                            d2 = rn_fma(dy, dy, d2);
-                            d2 = rn_fma(dz, dz, d2);
-                            sure_rej = mac_lh >= d2;
+                            if (ph1) {
+                                F dmax2 = F(0);
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) {
+                                    const F far = fmax(c[j] - blo[j], bhi[j] - c[j]);
+                                    dmax2 = fma(far, far, dmax2);
+                                }
+                                sure_rej = mac_lh >= dmax2 * (F(1) + F(9.5367431640625e-07));
+                                fr = !sure_rej;
+                            } else {
+                                const u32 q = (c[1] < bmid[1] ? 2u : 0u) + (c[2] < bmid[2] ? 1u : 0u);
+                                const u32 ci = ((c[0] < bmid[0] ? cand_neg : cand_pos) >> (8u * q)) & 0xffu;
+                                const vec4<F> t = tpos[ci];
+                                const F dx = rn_sub(na.x, t.x), dy = rn_sub(na.y, t.y), dz = rn_sub(na.z, t.z);
+                                F d2 = rn_mul(dx, dx);
+                                d2 = rn_fma(dy, dy, d2);
+                                d2 = rn_fma(dz, dz, d2);
+                                sure_rej = mac_lh >= d2;
+                            }
                         }
                     }
-                    const bool need = test && !sure_acc && !sure_rej;
+                    const bool need = test && !sure_acc && !sure_rej && !fr;
                     bool fail = !need;
                     if (__any_sync(FULL, need)) {
                         if (staged) {
@@ -658,10 +744,22 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     const bool rejected = sure_rej || (need && fail);
                     const bool open_leaf = rejected && nch == 0u;
                     const bool descend = is_anc || (rejected && nch != 0u);
-                    const u32 m_test = __ballot_sync(FULL, test), m_acc = __ballot_sync(FULL, accept),
+                    const u32 m_test = __ballot_sync(FULL, test && !fr), m_acc = __ballot_sync(FULL, accept),
                               m_leaf = __ballot_sync(FULL, open_leaf), m_desc = __ballot_sync(FULL, descend);
                     n_mac += __popc(m_test);
                     n_acc += __popc(m_acc);
+                    if (ph1) {
+                        // undecided / overlapping nodes -> frontier of the run
+                        const u32 m_fr = __ballot_sync(FULL, fr);
+                        if (m_fr) {
+                            if (fcount + 32u > FRONT_CAP) {
+                                fover = true;
+                            } else if (fr) {
+                                front[fcount + __popc(m_fr & ltm)] = k;
+                            }
+                            fcount += fover ? 0u : __popc(m_fr);
+                        }
+                    }
                     // accepted nodes -> ring
                     if (accept) {
                         ring[(lhead + lcount + __popc(m_acc & ltm)) & (LCAP - 1)] = na;
@@ -690,11 +788,11 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                         n_p2p += lq_total;
                     }
                     __syncwarp();
-                    if (overflow) {
+                    if (overflow || fover) {
                         done = true;
                     }
                 }
-                if (lcount == 0u) {
+                if (lcount == 0u || fover) {
                     break;
                 }
                 // ---------------- consume: evaluate up to 32 sources (the only ring call site) ----------------
@@ -717,16 +815,34 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
             if (overflow && lane == 0) {
                 atomicExch(p.err, 1u);
             }
-
-            // self interactions inside the group, tree.hpp:2073-2321 (sources = the group's own particles)
-            if (staged) {
-                eval_slots<F, Q, true>(tgt, T, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+            if (ph1) {
+                cp_async_wait_all();
+                __syncwarp();
+                if (fover) {
+                    // more frontier nodes than the buffer holds: this run's groups walk from the root instead
+                    fcount = 1u;
+                    if (lane == 0) {
+                        front[0] = 0u;
+                    }
+                    __syncwarp();
+                    break;
+                }
+                have_partial = true;
+                n_mac1 = n_mac;
+                n_acc1 = n_acc;
+                n_p2p1 = n_p2p;
             } else {
-                eval_slots<F, Q, true>(gsrc, T, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                // self interactions inside the group, tree.hpp:2073-2321 (sources = the group's own particles)
+                if (staged) {
+                    eval_slots<F, Q, true>(tgt, T, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                } else {
+                    eval_slots<F, Q, true>(gsrc, T, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
+                }
             }
 
-            // Combine the slices' partial sums (fixed shuffle tree: deterministic), apply G as one final multiply
-            // (tree.hpp:2986-3002) and write out (3004-3007).
+            // Combine the slices' partial sums (fixed shuffle tree: deterministic). Phase 1 parks the run's partial
+            // sums in the output arrays; a group adds them to its own, applies G as one final multiply
+            // (tree.hpp:2986-3002) and writes out (3004-3007).
             for (u32 k = 0; k < rr; ++k) {
                 vec4<F> a = acc_lane[32u * k];
                 for (u32 o = P; o < 32u; o <<= 1) {
@@ -738,11 +854,32 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 const u32 i = t0 + P * k + tl;
                 if (sl == 0u && i < t0 + tc) {
                     u32 dst = gb + i;
-                    const F tmass = tpos[i].w;
                     if (p.perm) {
                         dst = p.perm[dst];
                     }
                     dst -= p.out_offset;
+                    if (ph1) {
+                        if (Q == 0 || Q == 2) {
+                            p.out[0][dst] = a.x;
+                            p.out[1][dst] = a.y;
+                            p.out[2][dst] = a.z;
+                        }
+                        if (Q != 0) {
+                            p.out[Q == 1 ? 0 : 3][dst] = a.w;
+                        }
+                        continue;
+                    }
+                    if (have_partial) {
+                        if (Q == 0 || Q == 2) {
+                            a.x += p.out[0][dst];
+                            a.y += p.out[1][dst];
+                            a.z += p.out[2][dst];
+                        }
+                        if (Q != 0) {
+                            a.w += p.out[Q == 1 ? 0 : 3][dst];
+                        }
+                    }
+                    const F tmass = tpos[i].w;
                     if (Q == 0 || Q == 2) {
                         p.out[0][dst] = a.x * p.G;
                         p.out[1][dst] = a.y * p.G;
@@ -756,20 +893,22 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     }
                 }
             }
-            if (t0 == 0 && lane == 0) {
+            if (!ph1 && t0 == 0 && lane == 0) {
+                const u32 t_mac = n_mac + n_mac1, t_acc = n_acc + n_acc1, t_p2p = n_p2p + n_p2p1;
                 if (p.group_cost) {
-                    p.group_cost[g] = u64(T) * (u64(n_p2p) + n_acc + u64(T) - 1u);
+                    p.group_cost[g] = u64(T) * (u64(t_p2p) + t_acc + u64(T) - 1u);
                 }
                 if (p.counters) {
-                    atomicAdd(p.counters + 0, u64(n_mac));
-                    atomicAdd(p.counters + 1, u64(n_acc));
-                    atomicAdd(p.counters + 2, u64(n_p2p) * T);
+                    atomicAdd(p.counters + 0, u64(t_mac));
+                    atomicAdd(p.counters + 1, u64(t_acc));
+                    atomicAdd(p.counters + 2, u64(t_p2p) * T);
                     atomicAdd(p.counters + 3, u64(T) * (u64(T) - 1u) / 2u);
-                    atomicAdd(p.counters + 4, u64(n_acc) * T);
+                    atomicAdd(p.counters + 4, u64(t_acc) * T);
                 }
             }
             n_mac = n_acc = n_p2p = 0; // count the first pass only
             __syncwarp();
+        }
         }
     }
 }
@@ -888,6 +1027,19 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st)
 }
 
 } // namespace
+
+#ifndef RK_TWO_PHASE
+#define RK_TWO_PHASE 1
+#endif
+u32 trav_window(u32 tmax, size_t max_group)
+{
+    // phase 1 keeps one accumulator per target of the run in the staged-target + accumulator areas of the warp:
+    // a window of W particles holds groups that end before W + max_group - 1 <= (tmax + acc_entries) targets
+    if (!RK_TWO_PHASE || max_group > tmax) {
+        return 0u;
+    }
+    return acc_entries(tmax); // = 32 * rr_cap1 - tmax
+}
 
 template <typename F>
 void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cudaStream_t st)
