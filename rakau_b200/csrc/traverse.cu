@@ -82,7 +82,7 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #define RK_STACK 512
 #endif
 constexpr int STACK_CAP = RK_STACK;   // (first child, count) entries per warp (<= 32 pushes per step, depth <= 21)
-constexpr int FRONT_CAP = 128;        // frontier nodes of a run of sibling groups (two-phase walk, see traverse_kernel)
+constexpr int FRONT_CAP = 160;        // frontier nodes of a run of sibling groups (two-phase walk, see traverse_kernel)
 constexpr u32 FULL = 0xffffffffu;
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
@@ -379,8 +379,9 @@ __device__ __forceinline__ u32 warp_lower_bound(const u32 *__restrict__ arr, u32
         const u32 step = (n + 32u) / 33u, idx = lo + (static_cast<u32>(lane) + 1u) * step - 1u;
         const bool less = idx < lo + n && arr[idx] < x;
         const u32 c = __popc(__ballot_sync(FULL, less)); // probes below x form a prefix of the lanes
+        // lane c's probe (if it exists) is the first one known to be >= x
         const u32 nlo = lo + c * step, nhi = lo + (c + 1u) * step - 1u;
-        n = (nhi < lo + n ? nhi : lo + n) - nlo;
+        n = (c < 32u && nhi < lo + n ? nhi : lo + n) - nlo;
         lo = nlo;
     }
     return lo;

@@ -124,6 +124,7 @@ for variant in ("box", "exact"):
         S["frontier"] += len(frontier); S["fmax"] = max(S["fmax"], len(frontier))
         # phase 2
         for k, g in enumerate(gs):
+            S["inter2"] = S.get("inter2", 0) + len(T[k]) * (len(T[k]) - 1)
             st = list(frontier)
             while st:
                 i = st.pop(); S["p2_visits"] += 1
@@ -133,11 +134,13 @@ for variant in ("box", "exact"):
                 size = box / 2.0 ** lvl[i]; mac_lh = size * size / theta2
                 d2 = ((T[k] - props[i, :3]) ** 2).sum(1)
                 if (mac_lh < d2).all():
-                    S["p2_src"] += 1
+                    S["p2_src"] += 1; S["inter2"] = S.get("inter2", 0) + len(T[k])
                 elif nd[i] == 0:
-                    S["p2_src"] += end[i] - beg[i]
+                    S["p2_src"] += end[i] - beg[i]; S["inter2"] = S.get("inter2", 0) + len(T[k]) * (end[i] - beg[i])
                 else:
                     st.extend(children(i))
+    S["inter2"] = S.get("inter2", 0) + S["inter_shared"]
+    assert S["inter2"] == S["inter"], "the two-phase walk must reproduce the per-group interaction count exactly"
     print(variant, S)
     print(f"  visits per group: baseline {S['base_visits']/S['groups']:.0f}; two-phase {(S['p1_visits']+S['p2_visits'])/S['groups']:.0f}"
           f" (phase 1 {S['p1_visits']/S['runs']:.0f} per run, phase 2 {S['p2_visits']/S['groups']:.0f} per group)"

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "plummer*.npz")))
 TOPO = ("begin", "end", "n_children", "code", "level")
 
 
