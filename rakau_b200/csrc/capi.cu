@@ -609,6 +609,7 @@ public:
         p.crit_begin = m_b.crit_begin.p;
         p.c0 = static_cast<u32>(c0);
         p.c1 = static_cast<u32>(c1);
+        p.ncrit = static_cast<u32>(C);
         p.work_counter = m_work.p;
         for (int l = 0; l < NLEVELS; ++l) {
             const F nd = m_box / static_cast<F>(u64(1) << l); // get_node_dim, tree.hpp:443-448
@@ -876,6 +877,7 @@ public:
         p.crit_begin = m_b.crit_begin.p;
         p.c0 = static_cast<u32>(c0);
         p.c1 = static_cast<u32>(C);
+        p.ncrit = static_cast<u32>(C);
         p.work_counter = m_work.p;
         for (int l = 0; l < NLEVELS; ++l) {
             p.mac_tab[l] = (m_mac == RK_MAC_BH) ? tab[l] * mac_value : tab[l];

@@ -239,6 +239,7 @@ struct trav_params {
     const u32 *crit_node;
     const u32 *crit_begin;
     u32 c0, c1;        // critical-node range
+    u32 ncrit;         // all critical nodes of the tree
     u32 *work_counter; // zeroed before launch
     F mac_tab[NLEVELS]; // bh: dim2(level) * theta^-2 ; bh_geom: dim(level)
     F mac_value, eps2, G;

@@ -40,6 +40,9 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace rk
 {
 
@@ -82,7 +85,6 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #define RK_STACK 512
 #endif
 constexpr int STACK_CAP = RK_STACK;   // (first child, count) entries per warp (<= 32 pushes per step, depth <= 21)
-constexpr int FRONT_CAP = 160;        // frontier nodes of a run of sibling groups (two-phase walk, see traverse_kernel)
 constexpr u32 FULL = 0xffffffffu;
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
@@ -368,7 +370,7 @@ __host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax, u32 LCAP)
 {
     // ring + staged targets + accumulators + stack + queues
     return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(acc_entries(tmax)) * sizeof(vec4<F>)
-           + size_t(STACK_CAP) * 4 + size_t(FRONT_CAP) * 4 + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
+           + size_t(STACK_CAP) * 4 + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
 }
 
 // First index j in [a, b) with arr[j] >= x, else b; the 32 lanes probe 32 positions per round (monotone array).
@@ -415,8 +417,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
     u32 *stack = reinterpret_cast<u32 *>(acc + acc_entries(p.tmax));
     const u32 rr_cap = acc_entries(p.tmax) / 32u;              // accumulator slots per lane (one group)
     const u32 rr_cap1 = (p.tmax + acc_entries(p.tmax)) / 32u; // phase 1: the staged-target area holds accumulators too
-    u32 *front = stack + STACK_CAP;
-    u32 *lq_incl = front + FRONT_CAP;
+    // the run's frontier lives at the top of the stack array and grows downwards: front(i) = stack_top[-i]
+    u32 *stack_top = stack + (STACK_CAP - 1);
+    u32 *lq_incl = stack + STACK_CAP;
     u32 *lq_base = lq_incl + 32;
     const u32 ltm = lanemask_lt();
     const F eps2 = p.eps2;
@@ -433,28 +436,32 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
         if (u >= n_units) {
             break;
         }
-        u32 j0 = p.c0 + u, j1 = j0 + 1u;
+        // [j0, j1): the run (ALL the groups of the window, so that phase 1 - and with it every result bit - does not
+        // depend on how the critical nodes are cut into launches or ranks); [e0, e1): its groups inside [c0, c1)
+        u32 j0 = p.c0 + u, j1 = j0 + 1u, e0 = j0, e1 = j1;
         if (W) {
             const u32 lo = (win0 + u) * W;
-            j0 = warp_lower_bound(p.crit_begin, p.c0, p.c1, lo, lane);
-            const u32 lim = p.c1 - j0 < W ? p.c1 : j0 + W; // a window holds at most W groups
+            j0 = warp_lower_bound(p.crit_begin, 0u, p.ncrit, lo, lane);
+            const u32 lim = p.ncrit - j0 < W ? p.ncrit : j0 + W; // a window holds at most W groups
             j1 = warp_lower_bound(p.crit_begin, j0, lim, lo + W, lane);
-            if (j0 == j1) {
+            e0 = j0 > p.c0 ? j0 : p.c0;
+            e1 = j1 < p.c1 ? j1 : p.c1;
+            if (e0 >= e1) {
                 continue;
             }
         }
-        const u32 ng = j1 - j0;
-        // stage 0 = phase 1 of the run (skipped for a single group: the walk then starts at the root), stages 1..ng =
-        // its groups
+        // stage 0 = phase 1 of the run (skipped for a single group: the walk then starts at the root), then the
+        // groups e0 .. e1 - 1
         u32 fcount = 1u;                       // frontier size; {root} unless phase 1 fills it
         u32 n_mac1 = 0, n_acc1 = 0, n_p2p1 = 0; // phase-1 tests / accepted nodes / leaf particles: shared by all groups
         bool have_partial = false;
         if (lane == 0) {
-            front[0] = 0u;
+            stack_top[0] = 0u;
         }
-        for (u32 s = ng > 1u ? 0u : 1u; s <= ng; ++s) {
+        const u32 fb = p.crit_begin[e0], fe = p.crit_begin[e1]; // targets whose results this launch writes
+        for (u32 s = j1 - j0 > 1u ? 0u : 1u; s <= e1 - e0; ++s) {
         const bool ph1 = s == 0u;
-        const u32 g = ph1 ? j0 : j0 + s - 1u;
+        const u32 g = ph1 ? j0 : e0 + s - 1u;
         const u32 gnode = ph1 ? 0xffffffffu : p.crit_node[g], gb = p.crit_begin[g], ge = p.crit_begin[ph1 ? j1 : g + 1u],
                   T = ge - gb;
         const bool staged = !ph1 && T <= p.tmax;
@@ -599,7 +606,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     } else if (fpos < fend) {
                         // ---- the stack is empty: the next 32 frontier nodes ----
                         have = fpos + static_cast<u32>(lane) < fend;
-                        k = front[have ? fpos + static_cast<u32>(lane) : 0u];
+                        k = *(stack_top - (have ? fpos + static_cast<u32>(lane) : 0u));
                         fpos += 32u;
                     } else {
                         done = true;
@@ -753,10 +760,10 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                         // undecided / overlapping nodes -> frontier of the run
                         const u32 m_fr = __ballot_sync(FULL, fr);
                         if (m_fr) {
-                            if (fcount + 32u > FRONT_CAP) {
+                            if (sp + fcount + 64u > STACK_CAP) { // (room for this step's 32 pushes as well)
                                 fover = true;
                             } else if (fr) {
-                                front[fcount + __popc(m_fr & ltm)] = k;
+                                *(stack_top - (fcount + __popc(m_fr & ltm))) = k;
                             }
                             fcount += fover ? 0u : __popc(m_fr);
                         }
@@ -768,7 +775,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     lcount += __popc(m_acc);
                     // rejected internal nodes / ancestors -> stack
                     if (m_desc) {
-                        if (sp + 32u > STACK_CAP) {
+                        if (sp + 32u + (ph1 ? fcount : fend) > STACK_CAP) {
                             overflow = true;
                         } else if (descend) {
                             stack[sp + __popc(m_desc & ltm)] = (nb.z << 3) | (nch - 1u);
@@ -823,7 +830,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     // more frontier nodes than the buffer holds: this run's groups walk from the root instead
                     fcount = 1u;
                     if (lane == 0) {
-                        front[0] = 0u;
+                        stack_top[0] = 0u;
                     }
                     __syncwarp();
                     break;
@@ -853,7 +860,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     a.w += __shfl_xor_sync(FULL, a.w, o);
                 }
                 const u32 i = t0 + P * k + tl;
-                if (sl == 0u && i < t0 + tc) {
+                if (sl == 0u && i < t0 + tc && (!ph1 || (gb + i >= fb && gb + i < fe))) {
                     u32 dst = gb + i;
                     if (p.perm) {
                         dst = p.perm[dst];
@@ -1006,6 +1013,12 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st)
     const int occ64 = trav_occupancy<F, Q, MAC, 64>(p.tmax, smem64), occ32 = trav_occupancy<F, Q, MAC, 32>(p.tmax, smem32);
     const bool big = occ64 >= occ32 && occ64 > 0;
     int per_sm = big ? occ64 : occ32;
+    static const bool debug = std::getenv("RK_DEBUG_LAUNCH") != nullptr;
+    if (debug) {
+        std::fprintf(stderr, "[rk] traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> CTAs/SM %d (64: %d with %zu B, 32: %d with %zu B) tmax %u window %u\n",
+                     sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? 64 : 32, per_sm, occ64, smem64, occ32, smem32, p.tmax,
+                     p.window);
+    }
     if (per_sm < 1) {
         throw cuda_error(1, "the traversal kernel does not fit on this device");
     }
