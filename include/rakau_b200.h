@@ -181,6 +181,17 @@ RK_API int rk_tree_crit_begin_at(rk_tree *t, const size_t *idx, size_t k, uint64
 RK_API int rk_tree_get_group_costs(rk_tree *t, uint64_t *costs);
 /* Device pointer to the same per-critical-node costs (uint64_t[ncrit]); NULL before the first evaluation. */
 RK_API const void *rk_tree_group_costs_device(rk_tree *t);
+/* First critical node whose first particle is >= particle_idx[j] (ncrit if none), k <= 16: re-snaps cuts kept as
+ * particle indices to the critical nodes of a rebuilt tree (the reference snaps its split the same way,
+ * tree.hpp:3168-3178). */
+RK_API int rk_tree_crit_lower_bound(rk_tree *t, const uint64_t *particle_idx, size_t k, uint64_t *out);
+/* Order-independent 64-bit fingerprints of the device-resident arrays: codes, perm, particles (Morton order), node
+ * topology (begin, end, first child, level | children), node properties (com, mass), critical node indices, critical
+ * node first particles, (n_nodes << 32) ^ n_crit. Two trees with equal fingerprints are equal bit for bit (up to
+ * hash collisions): the multi-GPU path checks its tree against the single-GPU build with it. */
+RK_API int rk_tree_digest(rk_tree *t, uint64_t out[8]);
+/* Name and launch configuration of the traversal kernel variant the last evaluation of this tree launched. */
+RK_API const char *rk_tree_last_kernel(const rk_tree *t);
 /* exact_acc_pot_impl, tree.hpp:3531-3569: direct sum for one particle. idx in Morton order (ordered=0) or
  * original order (ordered=1). out4 = ax, ay, az, pot. */
 RK_API int rk_tree_exact(rk_tree *t, size_t idx, int ordered, double G, double eps, double out4[4]);
@@ -215,6 +226,8 @@ RK_API unsigned long long rk_kernel_launch_count(void);
 /* FFMA microbenchmark on `device`: measured FP32-pipe peak in TFLOP/s (2 flop per FFMA), the denominator of the
  * traversal roofline (do not assume the nominal clock). */
 RK_API int rk_measure_fp32_peak(int device, double *tflops, double *ms);
+/* The same with DFMA: the FP64-pipe peak (config 3). */
+RK_API int rk_measure_fp64_peak(int device, double *tflops, double *ms);
 
 #ifdef __cplusplus
 }

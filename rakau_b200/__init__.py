@@ -35,6 +35,7 @@ SYMBOLS = [
     "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak", "rk_device_copy_async",
     "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
     "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
+    "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak",
 ]
 
 
@@ -120,6 +121,11 @@ def lib():
     L.rk_tree_get_codes_device.argtypes = [vp, vp]
     L.rk_tree_build_presorted.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, dbl, sz, sz, vp, C.POINTER(BuildInfo)]
     L.rk_tree_crit_begin_at.argtypes = [vp, vp, sz, vp]
+    L.rk_tree_crit_lower_bound.argtypes = [vp, vp, sz, vp]
+    L.rk_tree_digest.argtypes = [vp, vp]
+    L.rk_tree_last_kernel.restype = C.c_char_p
+    L.rk_tree_last_kernel.argtypes = [vp]
+    L.rk_measure_fp64_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.rk_deduce_box.restype = dbl
     L.rk_deduce_box.argtypes = [i32, dbl]
     _LIB = L
@@ -279,6 +285,22 @@ class Octree:
         self._check(self.L.rk_tree_crit_begin_at(self.h, _ptr(idx), idx.size, _ptr(out)))
         return out
 
+    def crit_lower_bound(self, particle_idx):
+        """First critical node whose first particle is >= each given particle index (<= 16 values)."""
+        idx = np.ascontiguousarray(particle_idx, dtype=np.uint64)
+        out = np.empty(idx.size, dtype=np.uint64)
+        self._check(self.L.rk_tree_crit_lower_bound(self.h, _ptr(idx), idx.size, _ptr(out)))
+        return out
+
+    def digest(self):
+        """Fingerprints of the device arrays (codes, perm, particles, nodeB, nodeA, crit nodes, crit begins, sizes)."""
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self.L.rk_tree_digest(self.h, _ptr(out)))
+        return out
+
+    def last_kernel(self):
+        return self.L.rk_tree_last_kernel(self.h).decode()
+
     def group_costs_device_ptr(self):
         return self.L.rk_tree_group_costs_device(self.h)
 
@@ -337,6 +359,15 @@ def measure_fp32_peak(device=0):
     rc = lib().rk_measure_fp32_peak(device, C.byref(tf), C.byref(ms))
     if rc:
         raise RuntimeError("rk_measure_fp32_peak failed")
+    return tf.value
+
+
+def measure_fp64_peak(device=0):
+    """Measured FP64-pipe peak (TFLOP/s, DFMA = 2 flop) on `device`."""
+    tf, ms = C.c_double(), C.c_double()
+    rc = lib().rk_measure_fp64_peak(device, C.byref(tf), C.byref(ms))
+    if rc:
+        raise RuntimeError("rk_measure_fp64_peak failed")
     return tf.value
 
 

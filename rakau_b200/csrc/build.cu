@@ -1030,11 +1030,65 @@ void window_levels(i8 *a, i8 *bbuf, i8 *lvl, size_t n, size_t w, cudaStream_t st
     window_final_kernel<<<g, 256, 0, st>>>(in, lvl, n, w + 1 - k); count_launch();
 }
 
+__device__ __forceinline__ u64 mix64(u64 x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+__global__ void __launch_bounds__(256) digest_kernel(const u32 *__restrict__ w, size_t n, u64 *__restrict__ out)
+{
+    u64 h = 0;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        h += mix64((static_cast<u64>(i) << 32) ^ mix64(w[i]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        h += __shfl_xor_sync(0xffffffffu, h, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, h);
+    }
+}
+__global__ void lower_bound_kernel(const u32 *__restrict__ arr, size_t n, const u64 *__restrict__ x, size_t k,
+                                   u64 *__restrict__ out)
+{
+    const size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (j >= k) {
+        return;
+    }
+    size_t lo = 0, hi = n; // first i with arr[i] >= x[j]
+    while (lo < hi) {
+        const size_t mid = lo + (hi - lo) / 2;
+        if (arr[mid] < x[j]) {
+            lo = mid + 1;
+        } else {
+            hi = mid;
+        }
+    }
+    out[j] = lo;
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------
+void launch_digest(const void *a, size_t bytes, u64 *out, cudaStream_t st)
+{
+    if (bytes >= 4) {
+        digest_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const u32 *>(a), bytes / 4, out); count_launch();
+    }
+}
+void launch_lower_bound(const u32 *arr, size_t n, const u64 *x, size_t k, u64 *out, cudaStream_t st)
+{
+    if (k) {
+        lower_bound_kernel<<<div_up(k, 64), 64, 0, st>>>(arr, n, x, k, out); count_launch();
+    }
+}
 constexpr unsigned STREAM_GRID = 148 * 8; // grid-stride kernels: a multiple of the SM count
 
 template <typename F>

@@ -70,7 +70,7 @@ public:
         RK_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m_hpin), 64 * sizeof(u64)));
         m_b.d_err.reserve(2);
         m_b.d_misc.reserve(8);
-        m_counters.reserve(8);
+        m_counters.reserve(40);
         m_work.reserve(8);
     }
     ~tree()
@@ -128,6 +128,7 @@ public:
         m_max_group = 0;
         m_costs_valid = false;
         m_cuts_valid = false;
+        m_have_inv = false; // sort_shard / traverse_external write a new permutation
         m_h_crit_begin.clear();
     }
 
@@ -630,6 +631,15 @@ public:
         p.err = m_work.p + 1;
         p.out_offset = 0;
         p.window = trav_window(p.tmax, m_max_group);
+        if (p.window) {
+            // tail work stealing (traverse.cu): records + frontiers of the last wave of runs
+            m_steal.reserve(size_t(TRAV_STEAL_SLOTS) * 16 + 16 + size_t(TRAV_STEAL_SLOTS) * trav_stack_cap());
+            p.steal = m_steal.p;
+            p.steal_published = m_steal.p + size_t(TRAV_STEAL_SLOTS) * 16;
+            p.steal_front = p.steal_published + 16;
+            p.steal_k = TRAV_STEAL_SLOTS;
+            RK_CUDA_CHECK(cudaMemsetAsync(m_steal.p, 0, (size_t(TRAV_STEAL_SLOTS) * 16 + 16) * sizeof(u32), m_stream));
+        }
         for (int j = 0; j < nres; ++j) {
             if (where == RK_DEVICE) {
                 p.out[j] = static_cast<F *>(out[j]);
@@ -650,15 +660,18 @@ public:
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
         // particle range covered by [c0, c1)
         size_t pb = 0, pe = n;
-        if (partial) {
-            host_crit_begin();
-            pb = m_h_crit_begin[c0];
-            pe = m_h_crit_begin[c1];
+        if (partial && where == RK_HOST) {
+            // only host outputs need the particle range; two entries through the pinned scratch, not the whole list
+            const size_t idx[2] = {c0, c1};
+            uint64_t be[2];
+            crit_begin_at(idx, 2, be);
+            pb = be[0];
+            pe = be[1];
         }
         unsigned launches = 1;
         const bool pipelined = where == RK_HOST && !ordered && (pe - pb) >= (size_t(1) << 20);
         if (!pipelined) {
-            launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream);
+            launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream, m_kernel_name);
             RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
             if (where == RK_HOST) {
                 for (int j = 0; j < nres; ++j) {
@@ -705,7 +718,10 @@ public:
                 q.c0 = static_cast<u32>(cuts[k]);
                 q.c1 = static_cast<u32>(cuts[k + 1]);
                 q.work_counter = m_work.p + 4 + k; // one work counter per launch
-                launch_traverse<F>(q, Q, m_mac, m_sm_count, st);
+                if (k != NCHUNK - 1) {
+                    q.steal = nullptr; // the next launch fills the SMs this one leaves: only the last one has a tail
+                }
+                launch_traverse<F>(q, Q, m_mac, m_sm_count, st, m_kernel_name);
                 RK_CUDA_CHECK(cudaEventRecord(m_chunk_ev[k], st));
                 ++launches;
             }
@@ -904,7 +920,7 @@ public:
         RK_CUDA_CHECK(cudaMemsetAsync(m_work.p, 0, 4 * sizeof(u32), m_stream));
         RK_CUDA_CHECK(cudaMemsetAsync(m_counters.p, 0, 8 * sizeof(u64), m_stream));
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
-        launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream);
+        launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream, m_kernel_name);
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
         for (int j = 0; j < nres; ++j) {
             F *dst = static_cast<F *>(out[j]) + (offset_output ? first : 0);
@@ -961,6 +977,45 @@ public:
         RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 16, d, 4 * sizeof(double), cudaMemcpyDeviceToHost, m_stream));
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
         std::memcpy(out4, m_hpin + 16, 4 * sizeof(double));
+    }
+
+    const char *last_kernel() const { return m_kernel_name; }
+    // Order-independent fingerprints of the device arrays (multi-GPU parity checks without moving the tree to the host).
+    void digest(uint64_t out[8])
+    {
+        use();
+        const size_t n = m_b.n, M = m_b.n_nodes, C = m_b.n_crit;
+        u64 *d = reinterpret_cast<u64 *>(m_counters.p);
+        RK_CUDA_CHECK(cudaMemsetAsync(d, 0, 8 * sizeof(u64), m_stream));
+        if (n) {
+            launch_digest(m_b.codes, n * sizeof(u64), d + 0, m_stream);
+            launch_digest(m_b.perm.p, n * sizeof(u32), d + 1, m_stream);
+            launch_digest(m_b.psorted.p, n * sizeof(vec4<F>), d + 2, m_stream);
+            launch_digest(m_b.nodeB.p, M * sizeof(uint4), d + 3, m_stream);
+            launch_digest(m_b.nodeA.p, M * sizeof(vec4<F>), d + 4, m_stream);
+            launch_digest(m_b.crit_node.p, C * sizeof(u32), d + 5, m_stream);
+            launch_digest(m_b.crit_begin.p, (C + 1) * sizeof(u32), d + 6, m_stream);
+        }
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 24, d, 8 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        std::memcpy(out, m_hpin + 24, 7 * sizeof(u64));
+        out[7] = (static_cast<u64>(M) << 32) ^ C;
+    }
+    // First critical node whose first particle is >= pidx[j] (ncrit if none): re-snaps particle-index cuts to the
+    // critical nodes of a rebuilt tree.
+    void crit_lower_bound(const uint64_t *pidx, size_t k, uint64_t *out)
+    {
+        use();
+        if (k > 16) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_crit_lower_bound: at most 16 values per call");
+        }
+        u64 *d = reinterpret_cast<u64 *>(m_counters.p);
+        std::memcpy(m_hpin + 32, pidx, k * sizeof(u64));
+        RK_CUDA_CHECK(cudaMemcpyAsync(d, m_hpin + 32, k * sizeof(u64), cudaMemcpyHostToDevice, m_stream));
+        launch_lower_bound(m_b.crit_begin.p, m_b.n_crit, d, k, d + 16, m_stream);
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 32, d + 16, k * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        std::memcpy(out, m_hpin + 32, k * sizeof(u64));
     }
 
 private:
@@ -1253,11 +1308,12 @@ private:
     size_t m_max_leaf_n = 16, m_ncrit = 128, m_max_group = 0;
     dbuf<F> m_out[4];
     dbuf<u64> m_group_cost, m_counters;
-    dbuf<u32> m_work;
+    dbuf<u32> m_work, m_steal;
     bool m_costs_valid = false, m_have_inv = false, m_pending_check_encode = false;
     F m_pending_inv_box = F(0);
     u64 *m_hpin = nullptr; // pinned scratch for small read-backs
     std::vector<u32> m_h_crit_begin;
+    char m_kernel_name[96] = "";
 };
 
 } // namespace rk
@@ -1525,6 +1581,22 @@ const void *rk_tree_group_costs_device(rk_tree *t)
     return t->fp == 32 ? t->t32->group_costs_device() : t->t64->group_costs_device();
 }
 
+int rk_tree_digest(rk_tree *t, uint64_t out[8])
+{
+    return guarded(t, [&]() { RK_WITH(t, T.digest(out)); });
+}
+int rk_tree_crit_lower_bound(rk_tree *t, const uint64_t *particle_idx, size_t k, uint64_t *out)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.crit_lower_bound(particle_idx, k, out)); });
+}
+const char *rk_tree_last_kernel(const rk_tree *t)
+{
+    if (!t) {
+        return "";
+    }
+    return t->fp == 32 ? t->t32->last_kernel() : t->t64->last_kernel();
+}
+
 int rk_device_copy_async(void *dst, const void *src, size_t bytes, void *stream)
 {
     if (!bytes) {
@@ -1548,6 +1620,24 @@ int rk_measure_fp32_peak(int device, double *tflops, double *ms)
         RK_CUDA_CHECK(cudaSetDevice(device));
         float t = 0;
         const double flops = rk::ffma_microbench(&t);
+        if (tflops) {
+            *tflops = flops / (double(t) * 1e-3) / 1e12;
+        }
+        if (ms) {
+            *ms = t;
+        }
+        return RK_OK;
+    } catch (...) {
+        return RK_ERR_RUNTIME;
+    }
+}
+
+int rk_measure_fp64_peak(int device, double *tflops, double *ms)
+{
+    try {
+        RK_CUDA_CHECK(cudaSetDevice(device));
+        float t = 0;
+        const double flops = rk::dfma_microbench(&t);
         if (tflops) {
             *tflops = flops / (double(t) * 1e-3) / 1e12;
         }

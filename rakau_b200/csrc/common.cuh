@@ -206,6 +206,11 @@ void launch_perm_first(const u32 *last_perm, u32 *perm, u32 *inv_perm, size_t n,
 void launch_perm_compose(const u32 *old_perm, const u32 *last_perm, u32 *new_perm, u32 *inv_perm, size_t n,
                          cudaStream_t st);
 void launch_iota(u32 *p, size_t n, cudaStream_t st);
+// out += sum over the 32-bit words w_i of the array of mix64(i, w_i): an order-independent fingerprint of a device array
+// (bytes must be a multiple of 4).
+void launch_digest(const void *a, size_t bytes, u64 *out, cudaStream_t st);
+// out[j] = first index i in [0, n] with arr[i] >= x[j] (n if none).
+void launch_lower_bound(const u32 *arr, size_t n, const u64 *x, size_t k, u64 *out, cudaStream_t st);
 
 // Topology: fills delta/lvl_leaf/lvl_crit, tilecnt, rowtot. After it the host reads rowtot to size the nodes.
 template <typename F>
@@ -251,13 +256,22 @@ struct trav_params {
     u32 *err;        // stack overflow flag
     u32 out_offset;  // subtracted from the particle index when writing (external-tree drop-in)
     u32 window;      // two-phase walk: particles per run of sibling groups (trav_window()); 0 = one group per unit
+    // work stealing at the tail of a launch (NULL = off): steal_k records of 16 words (next group, groups, ready,
+    // frontier size, phase-1 counters, first group, partial flag), zeroed before the launch, + their frontiers
+    u32 *steal, *steal_front, *steal_published;
+    u32 steal_k;
 };
+constexpr unsigned TRAV_STEAL_SLOTS = 4096;
+// words per stolen frontier = the per-warp stack capacity of traverse.cu
+unsigned trav_stack_cap();
 // Window of the two-phase walk for groups of at most max_group targets (0 when a group exceeds the staging area).
 u32 trav_window(u32 tmax, size_t max_group);
+// name: NULL or a buffer of >= 96 bytes that receives the launched variant ("traverse_kernel<float,Q=0,...>").
 template <typename F>
-void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cudaStream_t st);
-// FFMA-bound microbenchmark on the current device: returns the flop count, *ms the CUDA-event time.
+void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cudaStream_t st, char *name = nullptr);
+// FFMA / DFMA-bound microbenchmarks on the current device: return the flop count, *ms the CUDA-event time.
 double ffma_microbench(float *ms);
+double dfma_microbench(float *ms);
 template <typename F>
 void launch_exact(const vec4<F> *parts, size_t n, size_t idx, F G, F eps2, double *d_out4, cudaStream_t st);
 

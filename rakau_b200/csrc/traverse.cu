@@ -75,6 +75,9 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #ifndef RK_CTAS
 #define RK_CTAS 5
 #endif
+#ifndef RK_STEAL
+#define RK_STEAL 1
+#endif
 #define RK_PRAGMA_(x) _Pragma(#x)
 #define RK_UNROLL_PRAGMA(n) RK_PRAGMA_(unroll n)
 // BATCH (template parameter of the kernel) = sources evaluated per consume step; the source ring holds 2 * BATCH
@@ -236,15 +239,18 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
 
 // NP pairs of target slots (slots 2k and 2k+1 of the tile; SINGLE: one slot, paired with itself and the upper half
 // discarded) against the sources src[jb, je).
-template <int Q, int NP, bool SINGLE>
+template <int Q, int NP, bool SINGLE, bool SELF>
 __device__ __forceinline__ void eval_tile_packed(const float4 *__restrict__ src, u32 jb, u32 je, float eps2,
                                                  const float4 *__restrict__ tpos, u32 T, u32 first_t, u32 P,
                                                  float4 *__restrict__ acc)
 {
     u64 tx[NP], ty[NP], tz[NP], ax[NP], ay[NP], az[NP], ap[NP];
+    u32 self0[NP], self1[NP];
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         const u32 t0i = first_t + P * (2 * k), t1i = SINGLE ? t0i : first_t + P * (2 * k + 1);
+        self0[k] = t0i;
+        self1[k] = t1i;
         // component-wise scalar loads straight into the two halves of each register pair (a float4 load would
         // leave the halves in different quads and ptxas re-packs them with MOVs inside the loop)
         const float *p0 = reinterpret_cast<const float *>(tpos + (t0i < T ? t0i : T - 1u)),
@@ -271,7 +277,12 @@ RK_UNROLL_PRAGMA(RK_UNROLL)
             d2 = fma2(dz, dz, d2);
             float d2a, d2b;
             upk2(d2, d2a, d2b);
-            const u64 inv = pk2(fast_rsqrt(d2a), fast_rsqrt(d2b));
+            float ia = fast_rsqrt(d2a), ib = fast_rsqrt(d2b);
+            if (SELF) { // the (i, i) pair
+                ia = (j == self0[k]) ? 0.f : ia;
+                ib = (j == self1[k]) ? 0.f : ib;
+            }
+            const u64 inv = pk2(ia, ib);
             if (Q != 1) {
                 const u64 ms = mul2(sm, mul2(mul2(inv, inv), inv));
                 ax[k] = fma2(dx, ms, ax[k]);
@@ -298,7 +309,7 @@ RK_UNROLL_PRAGMA(RK_UNROLL)
 }
 
 // fp32, non-self sources: all rr slots of this lane against the ring entries, two slots per register pair.
-template <int Q>
+template <int Q, bool SELF>
 __device__ __forceinline__ void eval_slots_packed(const float4 *__restrict__ src, u32 cnt, u32 sl, u32 ls, float eps2,
                                                   const float4 *__restrict__ tpos, u32 T, u32 t_lane, u32 P, u32 rr,
                                                   float4 *__restrict__ acc_lane)
@@ -308,27 +319,27 @@ __device__ __forceinline__ void eval_slots_packed(const float4 *__restrict__ src
 #if RK_NP4
 #pragma unroll 1
     for (; k + 8u <= rr; k += 8u) {
-        eval_tile_packed<Q, 4, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile_packed<Q, 4, false, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
     }
     if (k + 4u <= rr) {
-        eval_tile_packed<Q, 2, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile_packed<Q, 2, false, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
         k += 4u;
     }
 #else
 #pragma unroll 1
     for (; k + 4u <= rr; k += 4u) {
-        eval_tile_packed<Q, 2, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile_packed<Q, 2, false, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
     }
 #endif
     if (k + 2u <= rr) {
-        eval_tile_packed<Q, 1, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile_packed<Q, 1, false, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
         k += 2u;
     }
     if (k < rr) {
 #if RK_SINGLE_SCALAR
-        eval_tile<float, Q, 1, false>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile<float, Q, 1, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
 #else
-        eval_tile_packed<Q, 1, true>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
+        eval_tile_packed<Q, 1, true, SELF>(src, jb, je, eps2, tpos, T, t_lane + P * k, P, acc_lane + 32u * k);
 #endif
     }
 }
@@ -370,7 +381,7 @@ __host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax, u32 LCAP)
 {
     // ring + staged targets + accumulators + stack + queues
     return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(acc_entries(tmax)) * sizeof(vec4<F>)
-           + size_t(STACK_CAP) * 4 + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/;
+           + size_t(STACK_CAP) * 4 + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/ + 16 * 4 /*run state*/;
 }
 
 // First index j in [a, b) with arr[j] >= x, else b; the 32 lanes probe 32 positions per round (monotone array).
@@ -421,47 +432,149 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
     u32 *stack_top = stack + (STACK_CAP - 1);
     u32 *lq_incl = stack + STACK_CAP;
     u32 *lq_base = lq_incl + 32;
+    // state of the run this warp is attached to: kept in shared memory, it is only needed between stages
+    // (registers are what limits the evaluation loop)
+    u32 *rs = lq_base + 32;
+    enum { RS_J0, RS_J1, RS_E0, RS_NG, RS_SLOT, RS_FCOUNT, RS_MAC1, RS_ACC1, RS_P2P1, RS_PARTIAL, RS_NEED_PH1, RS_GI };
     const u32 ltm = lanemask_lt();
     const F eps2 = p.eps2;
     const u32 W = p.window;
     const u32 win0 = W ? p.crit_begin[p.c0] / W : 0u;
     const u32 n_units = W ? (p.crit_begin[p.c1] - 1u) / W - win0 + 1u : p.c1 - p.c0;
 
+    // Tail of the launch: a run is ~7 groups, a warp gets only ~5 runs of a 4M-particle evaluation, so the last runs
+    // would leave most warps idle while a few finish (9 % of the kernel time). The runs of the LAST WAVE (the final
+    // steal_k units of the queue) therefore publish their phase-1 state (frontier, counters; the partial sums are
+    // already in the output arrays) in global memory and hand out their groups through an atomic counter: a warp that
+    // finds the queue empty attaches to a published run and takes groups from it. Who evaluates a group does not
+    // change a single operation of its evaluation, so the results stay bit-identical.
+    constexpr u32 NONE = 0xffffffffu;
+    const u32 ksteal = (RK_STEAL && p.steal && W) ? (p.steal_k < n_units ? p.steal_k : n_units) : 0u;
+    bool queue_empty = false;
+
     for (;;) {
-        u32 u = 0;
-        if (lane == 0) {
-            u = atomicAdd(p.work_counter, 1u);
-        }
-        u = __shfl_sync(FULL, u, 0);
-        if (u >= n_units) {
-            break;
-        }
+        // ---- attach to a run: the next unit of the queue, or a published run of the last wave ----
         // [j0, j1): the run (ALL the groups of the window, so that phase 1 - and with it every result bit - does not
-        // depend on how the critical nodes are cut into launches or ranks); [e0, e1): its groups inside [c0, c1)
-        u32 j0 = p.c0 + u, j1 = j0 + 1u, e0 = j0, e1 = j1;
-        if (W) {
-            const u32 lo = (win0 + u) * W;
-            j0 = warp_lower_bound(p.crit_begin, 0u, p.ncrit, lo, lane);
-            const u32 lim = p.ncrit - j0 < W ? p.ncrit : j0 + W; // a window holds at most W groups
-            j1 = warp_lower_bound(p.crit_begin, j0, lim, lo + W, lane);
-            e0 = j0 > p.c0 ? j0 : p.c0;
-            e1 = j1 < p.c1 ? j1 : p.c1;
-            if (e0 >= e1) {
-                continue;
+        // depend on how the critical nodes are cut into launches or ranks); e0 .. e0 + ng - 1: its groups in [c0, c1)
+        u32 slot = NONE;
+        if (!queue_empty) {
+            u32 u = 0;
+            if (lane == 0) {
+                u = atomicAdd(p.work_counter, 1u);
+            }
+            u = __shfl_sync(FULL, u, 0);
+            if (u >= n_units) {
+                queue_empty = true;
+            } else {
+                u32 j0 = p.c0 + u, j1 = j0 + 1u, e0 = j0, ng = 1u;
+                if (W) {
+                    const u32 lo = (win0 + u) * W;
+                    j0 = warp_lower_bound(p.crit_begin, 0u, p.ncrit, lo, lane);
+                    const u32 lim = p.ncrit - j0 < W ? p.ncrit : j0 + W; // a window holds at most W groups
+                    j1 = warp_lower_bound(p.crit_begin, j0, lim, lo + W, lane);
+                    e0 = j0 > p.c0 ? j0 : p.c0;
+                    const u32 e1 = j1 < p.c1 ? j1 : p.c1;
+                    ng = e1 > e0 ? e1 - e0 : 0u;
+                }
+                // phase 1 is skipped for a single group: its walk then starts at the root
+                const bool need_ph1 = j1 - j0 > 1u && ng != 0u;
+                if (n_units - 1u - u < ksteal) {
+                    if (need_ph1) {
+                        slot = n_units - 1u - u; // published after phase 1
+                    } else if (lane == 0) {
+                        atomicAdd(p.steal_published, 1u); // nothing to share
+                    }
+                }
+                if (ng == 0u) {
+                    continue;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    stack_top[0] = 0u; // frontier = {root} unless phase 1 fills it
+                    rs[RS_J0] = j0;
+                    rs[RS_J1] = j1;
+                    rs[RS_E0] = e0;
+                    rs[RS_NG] = ng;
+                    rs[RS_SLOT] = slot;
+                    rs[RS_FCOUNT] = 1u;
+                    rs[RS_MAC1] = 0u; // phase-1 tests / accepted nodes / leaf particles: shared by all the groups
+                    rs[RS_ACC1] = 0u;
+                    rs[RS_P2P1] = 0u;
+                    rs[RS_PARTIAL] = 0u;
+                    rs[RS_NEED_PH1] = need_ph1 ? 1u : 0u;
+                    rs[RS_GI] = 0u;
+                }
+                __syncwarp();
             }
         }
-        // stage 0 = phase 1 of the run (skipped for a single group: the walk then starts at the root), then the
-        // groups e0 .. e1 - 1
-        u32 fcount = 1u;                       // frontier size; {root} unless phase 1 fills it
-        u32 n_mac1 = 0, n_acc1 = 0, n_p2p1 = 0; // phase-1 tests / accepted nodes / leaf particles: shared by all groups
-        bool have_partial = false;
-        if (lane == 0) {
-            stack_top[0] = 0u;
+        if (queue_empty) {
+            if (ksteal == 0u) {
+                break;
+            }
+            for (;;) {
+                const u32 pub = *static_cast<volatile u32 *>(p.steal_published); // read BEFORE the scan
+                for (u32 sb = 0; sb < ksteal && slot == NONE; sb += 32u) {
+                    const u32 si = sb + static_cast<u32>(lane);
+                    bool ok = false;
+                    if (si < ksteal) {
+                        const volatile u32 *h = p.steal + size_t(si) * 16u;
+                        ok = h[2] != 0u && h[0] < h[1];
+                    }
+                    const u32 m = __ballot_sync(FULL, ok);
+                    if (m) {
+                        slot = sb + static_cast<u32>(__ffs(m)) - 1u;
+                    }
+                }
+                if (slot != NONE || pub == ksteal) {
+                    break; // (pub == ksteal: every run of the last wave was resolved before the scan, none has work left)
+                }
+                __nanosleep(500);
+            }
+            if (slot == NONE) {
+                break;
+            }
+            __threadfence();
+            const volatile u32 *h = p.steal + size_t(slot) * 16u;
+            const u32 fc = h[3];
+            __syncwarp();
+            if (lane == 0) {
+                rs[RS_NG] = h[1];
+                rs[RS_FCOUNT] = fc;
+                rs[RS_MAC1] = h[4];
+                rs[RS_ACC1] = h[5];
+                rs[RS_P2P1] = h[6];
+                rs[RS_E0] = h[7];
+                rs[RS_PARTIAL] = h[8];
+                rs[RS_SLOT] = slot;
+                rs[RS_NEED_PH1] = 0u;
+                rs[RS_GI] = 0u;
+            }
+            for (u32 i = lane; i < fc; i += 32u) {
+                *(stack_top - i) = p.steal_front[size_t(slot) * STACK_CAP + i];
+            }
+            __syncwarp();
         }
-        const u32 fb = p.crit_begin[e0], fe = p.crit_begin[e1]; // targets whose results this launch writes
-        for (u32 s = j1 - j0 > 1u ? 0u : 1u; s <= e1 - e0; ++s) {
-        const bool ph1 = s == 0u;
-        const u32 g = ph1 ? j0 : e0 + s - 1u;
+        for (;;) {
+        const bool ph1 = rs[RS_NEED_PH1] != 0u;
+        u32 g = rs[RS_J0];
+        __syncwarp();
+        if (ph1) {
+            if (lane == 0) {
+                rs[RS_NEED_PH1] = 0u;
+            }
+        } else {
+            u32 gi = 0;
+            if (lane == 0) {
+                const u32 sl_ = rs[RS_SLOT];
+                gi = sl_ != NONE ? atomicAdd(p.steal + size_t(sl_) * 16u, 1u) : rs[RS_GI]++;
+            }
+            gi = __shfl_sync(FULL, gi, 0);
+            if (gi >= rs[RS_NG]) {
+                break;
+            }
+            g = rs[RS_E0] + gi;
+        }
+        const u32 j1 = rs[RS_J1];
         const u32 gnode = ph1 ? 0xffffffffu : p.crit_node[g], gb = p.crit_begin[g], ge = p.crit_begin[ph1 ? j1 : g + 1u],
                   T = ge - gb;
         const bool staged = !ph1 && T <= p.tmax;
@@ -533,6 +646,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
         const vec4<F> *tpos = staged ? tgt : gsrc;
         const F bmid[3] = {(blo[0] + bhi[0]) * F(0.5), (blo[1] + bhi[1]) * F(0.5), (blo[2] + bhi[2]) * F(0.5)};
         const u32 cap = ph1 ? rr_cap1 : rr_cap;
+        // phase 1 writes partial sums for the targets of this launch only
+        const u32 fb = ph1 ? p.crit_begin[rs[RS_E0]] : 0u, fe = ph1 ? p.crit_begin[rs[RS_E0] + rs[RS_NG]] : 0u;
         vec4<F> *acc_lane = (ph1 ? tgt : acc) + lane; // phase 1 reads its targets from global memory (L1)
         for (u32 t0 = 0; t0 < T; t0 += 32u * cap) {
             const u32 tc = (T - t0 < 32u * cap) ? (T - t0) : 32u * cap;
@@ -557,10 +672,10 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
 
             // phase 1 starts at the root; a group starts at the run's frontier (the root when there was no phase 1)
             u32 sp = ph1 ? 1u : 0u, fpos = 0u, lhead = 0, lcount = 0, lq_total = 0, lq_done = 0;
-            const u32 fend = ph1 ? 0u : fcount;
+            const u32 fend = ph1 ? 0u : rs[RS_FCOUNT];
+            u32 fcount = 0u; // phase 1: frontier nodes found so far
             bool done = false, overflow = false, fover = false;
             if (ph1) {
-                fcount = 0u;
                 if (lane == 0) {
                     stack[0] = 0u; // root: first = 0, count = 1
                 }
@@ -810,7 +925,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 if (RK_SKIP_EVAL && p.G != F(-12345)) {
                     // timing experiment: walk only
                 } else if constexpr (sizeof(F) == 4 && RK_PACKED) {
-                    eval_slots_packed<Q>(reinterpret_cast<const float4 *>(ring + lhead), ne, sl, 5u - lp, eps2,
+                    eval_slots_packed<Q, false>(reinterpret_cast<const float4 *>(ring + lhead), ne, sl, 5u - lp, eps2,
                                          reinterpret_cast<const float4 *>(tpos), T, t0 + tl, P, rr,
                                          reinterpret_cast<float4 *>(acc_lane));
                 } else {
@@ -828,20 +943,27 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 __syncwarp();
                 if (fover) {
                     // more frontier nodes than the buffer holds: this run's groups walk from the root instead
-                    fcount = 1u;
                     if (lane == 0) {
-                        stack_top[0] = 0u;
+                        stack_top[0] = 0u; // (RS_FCOUNT is still 1, the phase-1 counters 0, no partial sums)
                     }
                     __syncwarp();
                     break;
                 }
-                have_partial = true;
-                n_mac1 = n_mac;
-                n_acc1 = n_acc;
-                n_p2p1 = n_p2p;
+                if (lane == 0) {
+                    rs[RS_FCOUNT] = fcount;
+                    rs[RS_PARTIAL] = 1u;
+                    rs[RS_MAC1] = n_mac;
+                    rs[RS_ACC1] = n_acc;
+                    rs[RS_P2P1] = n_p2p;
+                }
+                __syncwarp();
             } else {
                 // self interactions inside the group, tree.hpp:2073-2321 (sources = the group's own particles)
-                if (staged) {
+                if constexpr (sizeof(F) == 4 && RK_PACKED) {
+                    eval_slots_packed<Q, true>(reinterpret_cast<const float4 *>(staged ? tgt : gsrc), T, sl, 5u - lp, eps2,
+                                               reinterpret_cast<const float4 *>(tpos), T, t0 + tl, P, rr,
+                                               reinterpret_cast<float4 *>(acc_lane));
+                } else if (staged) {
                     eval_slots<F, Q, true>(tgt, T, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
                 } else {
                     eval_slots<F, Q, true>(gsrc, T, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
@@ -860,7 +982,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                     a.w += __shfl_xor_sync(FULL, a.w, o);
                 }
                 const u32 i = t0 + P * k + tl;
-                if (sl == 0u && i < t0 + tc && (!ph1 || (gb + i >= fb && gb + i < fe))) {
+                if (sl == 0u && i < t0 + tc && (!ph1 || (gb + i >= fb && gb + i < fe))) { // (phase 1: in-range targets only)
                     u32 dst = gb + i;
                     if (p.perm) {
                         dst = p.perm[dst];
@@ -877,7 +999,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                         }
                         continue;
                     }
-                    if (have_partial) {
+                    if (rs[RS_PARTIAL]) {
                         if (Q == 0 || Q == 2) {
                             a.x += p.out[0][dst];
                             a.y += p.out[1][dst];
@@ -902,7 +1024,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 }
             }
             if (!ph1 && t0 == 0 && lane == 0) {
-                const u32 t_mac = n_mac + n_mac1, t_acc = n_acc + n_acc1, t_p2p = n_p2p + n_p2p1;
+                const u32 t_mac = n_mac + rs[RS_MAC1], t_acc = n_acc + rs[RS_ACC1], t_p2p = n_p2p + rs[RS_P2P1];
                 if (p.group_cost) {
                     p.group_cost[g] = u64(T) * (u64(t_p2p) + t_acc + u64(T) - 1u);
                 }
@@ -915,6 +1037,31 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
                 }
             }
             n_mac = n_acc = n_p2p = 0; // count the first pass only
+            __syncwarp();
+        }
+        if (ph1 && rs[RS_SLOT] != NONE) {
+            // publish the run: frontier + counters (the partial sums were written by the loop above)
+            const u32 slot_ = rs[RS_SLOT], fc = rs[RS_FCOUNT];
+            for (u32 i = lane; i < fc; i += 32u) {
+                p.steal_front[size_t(slot_) * STACK_CAP + i] = *(stack_top - i);
+            }
+            volatile u32 *h = p.steal + size_t(slot_) * 16u;
+            if (lane == 0) {
+                h[1] = rs[RS_NG];
+                h[3] = fc;
+                h[4] = rs[RS_MAC1];
+                h[5] = rs[RS_ACC1];
+                h[6] = rs[RS_P2P1];
+                h[7] = rs[RS_E0];
+                h[8] = rs[RS_PARTIAL];
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                h[2] = 1u; // ready
+                __threadfence();
+                atomicAdd(p.steal_published, 1u);
+            }
             __syncwarp();
         }
         }
@@ -989,6 +1136,29 @@ __global__ void __launch_bounds__(256) ffma_kernel(float *out, int iters, float 
     }
 }
 
+// FP64-pipe peak probe (same shape as ffma_kernel).
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b)
+{
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            v0 = fma(v0, a, b);
+            v1 = fma(v1, a, b);
+            v2 = fma(v2, a, b);
+            v3 = fma(v3, a, b);
+            v4 = fma(v4, a, b);
+            v5 = fma(v5, a, b);
+            v6 = fma(v6, a, b);
+            v7 = fma(v7, a, b);
+        }
+    }
+    const double s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    if (s == 123.456) {
+        out[0] = s;
+    }
+}
+
 template <typename F, int Q, int MAC, int BATCH>
 int trav_occupancy(u32 tmax, size_t &smem)
 {
@@ -1006,13 +1176,17 @@ int trav_occupancy(u32 tmax, size_t &smem)
 }
 
 template <typename F, int Q, int MAC>
-void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st)
+void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *name)
 {
     // batches of 64 sources unless the larger ring costs a resident CTA (tmax = 256)
     size_t smem64 = 0, smem32 = 0;
     const int occ64 = trav_occupancy<F, Q, MAC, 64>(p.tmax, smem64), occ32 = trav_occupancy<F, Q, MAC, 32>(p.tmax, smem32);
     const bool big = occ64 >= occ32 && occ64 > 0;
     int per_sm = big ? occ64 : occ32;
+    if (name) {
+        std::snprintf(name, 96, "traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> window=%u ctas_per_sm=%d",
+                      sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? 64 : 32, p.window, per_sm);
+    }
     static const bool debug = std::getenv("RK_DEBUG_LAUNCH") != nullptr;
     if (debug) {
         std::fprintf(stderr, "[rk] traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> CTAs/SM %d (64: %d with %zu B, 32: %d with %zu B) tmax %u window %u\n",
@@ -1045,6 +1219,8 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st)
 #ifndef RK_TWO_PHASE
 #define RK_TWO_PHASE 1
 #endif
+unsigned trav_stack_cap() { return STACK_CAP; }
+
 u32 trav_window(u32 tmax, size_t max_group)
 {
     // phase 1 keeps one accumulator per target of the run in the staged-target + accumulator areas of the warp:
@@ -1056,11 +1232,11 @@ u32 trav_window(u32 tmax, size_t max_group)
 }
 
 template <typename F>
-void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cudaStream_t st)
+void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cudaStream_t st, char *name)
 {
 #define RK_DISPATCH(QQ, MM)                                                                                            \
     if (Q == QQ && mac == MM) {                                                                                        \
-        launch_one<F, QQ, MM>(p, sm_count, st);                                                                        \
+        launch_one<F, QQ, MM>(p, sm_count, st, name);                                                                  \
         return;                                                                                                        \
     }
     RK_DISPATCH(0, 0)
@@ -1071,6 +1247,29 @@ void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cuda
     RK_DISPATCH(2, 1)
 #undef RK_DISPATCH
     throw cuda_error(1, "invalid Q / MAC combination");
+}
+
+double dfma_microbench(float *ms)
+{
+    int dev = 0, sms = 0;
+    RK_CUDA_CHECK(cudaGetDevice(&dev));
+    RK_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *d = nullptr;
+    RK_CUDA_CHECK(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    RK_CUDA_CHECK(cudaEventCreate(&e0));
+    RK_CUDA_CHECK(cudaEventCreate(&e1));
+    const int iters = 1024, grid = sms * 8;
+    dfma_kernel<<<grid, 256>>>(d, 16, 1.0001, 0.5); // warm-up
+    RK_CUDA_CHECK(cudaEventRecord(e0));
+    dfma_kernel<<<grid, 256>>>(d, iters, 1.0001, 0.5);
+    RK_CUDA_CHECK(cudaEventRecord(e1));
+    RK_CUDA_CHECK(cudaEventSynchronize(e1));
+    RK_CUDA_CHECK(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return 2.0 * 8 * 16 * double(iters) * 256.0 * grid;
 }
 
 double ffma_microbench(float *ms)
@@ -1103,8 +1302,8 @@ void launch_exact(const vec4<F> *parts, size_t n, size_t idx, F G, F eps2, doubl
     RK_CUDA_CHECK(cudaGetLastError());
 }
 
-template void launch_traverse<float>(const trav_params<float> &, int, int, int, cudaStream_t);
-template void launch_traverse<double>(const trav_params<double> &, int, int, int, cudaStream_t);
+template void launch_traverse<float>(const trav_params<float> &, int, int, int, cudaStream_t, char *);
+template void launch_traverse<double>(const trav_params<double> &, int, int, int, cudaStream_t, char *);
 template void launch_exact<float>(const vec4<float> *, size_t, size_t, float, float, double *, cudaStream_t);
 template void launch_exact<double>(const vec4<double> *, size_t, size_t, double, double, double *, cudaStream_t);
 
