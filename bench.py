@@ -7,14 +7,19 @@ evaluation = tree build (Morton encode, sort, octree, node properties) + ncrit-g
          bench.py --gpus N --steps K --warmup W
 
 N = 1: BASELINE config 1 (3D Plummer, 4M particles, fp32, theta = 0.75, accelerations, max_leaf_n 16,
-ncrit 128 — the parameters behind the reference's published table). N > 1: BASELINE config 5 (128M
-particles, strong scaling): inputs sharded over the ranks, all-gathered with NCCL, identical tree on every
-GPU, critical nodes sharded by cost-weighted Morton ranges, outputs all-gathered.
+ncrit 128 — the parameters behind the reference's published table). The same line carries, under "configs",
+driver-visible measurements of BASELINE configs 2 (accs+pots, eps, G), 3 (fp64, theta 0.5, FP64-pipe fraction),
+4 (16M leapfrog, device-resident and end to end) and the one-GPU base of config 5 (128M, same chunked generator
+as the N > 1 runs). N > 1: BASELINE config 5 (128M particles, strong scaling): inputs sharded over the ranks,
+distributed sample sort, identical tree on every GPU, critical nodes sharded by cost-weighted Morton ranges,
+outputs exchanged over peer memory; before timing, the sharded tree and the gathered accelerations are checked
+against a single-GPU evaluation of the same particles, bit for bit ("parity_checked").
 
 Prints ONE JSON line (rank 0). `value` = interactions / device time with inputs resident in HBM;
 `e2e` = the same through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region).
 `--impl reference` times the reference's CPU algorithm on the host cores (oracle/_ref when it was built,
-else the scalar oracle port) — the only place besides `cpu_baseline` where oracle/ is executed.
+else the scalar oracle port) — the only place besides `cpu_baseline` where oracle/ is executed; that arm does not
+load the product library.
 """
 import argparse
 import json
@@ -32,6 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "Ginteractions/s (accel eval = tree build + traversal, Plummer, theta=0.75, fp32; ms per accel eval in ms_per_step)"
 SLOTS_PER_INTERACTION = 12  # FP32 issue slots per pair (3 FADD + 3 FFMA + 3 FMUL + 3 FFMA), SURVEY §8(d) conv. B
 FLOP_PER_INTERACTION_LIT = 20  # literature convention A
+L2_NOTE = "GPU arm: 256 MiB device buffer written between timed iterations"
 
 
 def parse():
@@ -45,8 +51,21 @@ def parse():
     ap.add_argument("--max-leaf-n", type=int, default=16)
     ap.add_argument("--ncrit", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs 2/3/4/5-base blocks of the N = 1 line")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the single-GPU comparison")
+    ap.add_argument("--perturb", action="store_true",
+                    help="N > 1: move the particles a little between steps (cost-weighted cuts must survive a rebuild)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
+
+
+def workload_config(args, nparts):
+    """The workload, with the same keys and values in both arms (the driver compares them)."""
+    return {"workload": f"plummer_{nparts}_fp32_theta{args.theta}_accs", "nparts": nparts, "fp": 32, "theta": args.theta,
+            "max_leaf_n": args.max_leaf_n, "ncrit": args.ncrit, "mac": "bh", "G": 1.0, "eps": 0.0,
+            "generator": "benchmark/common.hpp:39-126, " + ("chunks of 2^20 particles, each seeded with its first index"
+                                                           if args.gpus > 1 else "sequential branch"),
+            "l2": L2_NOTE}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -67,6 +86,7 @@ class ClockSampler:
             self.f = open(self.path, "w")
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "20", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+            time.sleep(0.25)  # nvidia-smi needs ~0.2 s before its first sample
         except Exception:
             self.p = None
 
@@ -99,43 +119,58 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            # "under load": the upper half of the samples (idle gaps between steps pull the clock down)
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
         return out
 
 
 # ----------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline (the ONLY users of oracle/ in this file)
+# reference arm / cpu baseline (the ONLY users of oracle/ in this file; the product library is not imported here)
 # ----------------------------------------------------------------------------------------------------------
+def exact_interactions(args, nparts, chunk):
+    """Interactions of one evaluation of the reference's tree, when the committed fixture holds them (config 1:
+    tests/golden/baseline_sizes.json, counted by the oracle on the reference's own tree)."""
+    if chunk or nparts != 4_000_000 or args.theta != 0.75 or args.max_leaf_n != 16 or args.ncrit != 128:
+        return None
+    try:
+        fix = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_sizes.json")))
+        return float(fix["config1_fp32_accs"]["counters"]["interactions"])
+    except Exception:
+        return None
+
+
 def cpu_reference_run(args, nparts, steps, warmup, target_seconds, chunk=0):
     """Times the reference's CPU implementation of the path on the host cores.
 
     Preferred: oracle/_ref (the UNMODIFIED reference header compiled against dependency stand-ins, SIMD + rsqrt
     path, OpenMP-backed TBB stand-in) — kind "reference": every step is a full build + full accs_u of the
     workload. Fallback: the scalar oracle port on a strided sample of the critical nodes — kind "port".
-    Interactions per evaluation come from the oracle's counters on a strided sample of the same tree (the
-    reference has no interaction counter)."""
+    Interactions per evaluation: the committed exact count for config 1, else the oracle's counters on a strided
+    sample of the same tree (the reference has no interaction counter). Returns the steps actually timed."""
     import oracle  # noqa: test infrastructure, allowed here only
-    import rakau_b200 as rk
     cores = os.cpu_count() or 1
-    m, x, y, z = rk.plummer(nparts, 0, nparts, chunk=chunk) if chunk else rk.plummer(nparts)
-    t0 = time.time()
-    otree = oracle.OracleTree(x, y, z, m, max_leaf_n=args.max_leaf_n, ncrit=args.ncrit)
-    t_obuild = time.time() - t0
-    ncrit_nodes = len(otree.crit()[0])
-    # interactions of one evaluation, from a strided sample of the oracle's counters (exact when stride = 1)
-    cstride = max(1, ncrit_nodes // 8000)
-    t0 = time.time()
-    c = otree.acc_pot_sample(0, args.theta, cstride, cstride // 2, nthreads=cores)
-    t_probe = max(time.time() - t0, 1e-4)
-    i_total = float(c["interactions"]) * cstride
+    m, x, y, z = oracle.plummer(nparts, chunk=chunk, nthreads=cores)
+    i_total = exact_interactions(args, nparts, chunk)
+    i_note = "exact (tests/golden/baseline_sizes.json)"
+    otree, t_obuild, t_probe, cstride = None, 0.0, 0.0, 1
     variant = oracle.best_ref_variant()
+    if i_total is None or variant is None:
+        t0 = time.time()
+        otree = oracle.OracleTree(x, y, z, m, max_leaf_n=args.max_leaf_n, ncrit=args.ncrit)
+        t_obuild = time.time() - t0
+        ncrit_nodes = len(otree.crit()[0])
+        cstride = max(1, ncrit_nodes // 8000)
+        t0 = time.time()
+        c = otree.acc_pot_sample(0, args.theta, cstride, cstride // 2, nthreads=cores)
+        t_probe = max(time.time() - t0, 1e-4)
+        if i_total is None:
+            i_total = float(c["interactions"]) * cstride
+            i_note = f"the oracle's counters on every {cstride}-th critical node"
     nsteps = max(1, steps + warmup)
     if variant is not None:
         # pick the faster SIMD width on a small problem (AVX-512 is not always the faster one)
         cands = [v for v in ("avx512", "avx2") if oracle.ref_available(v) and (v != "avx512" or variant == "avx512")]
         if len(cands) > 1:
-            pm, px, py, pz = rk.plummer(200000)
+            pm, px, py, pz = oracle.plummer(200000)
             best = None
             for v in cands:
                 rt = oracle.RefTree(px, py, pz, pm, max_leaf_n=args.max_leaf_n, ncrit=args.ncrit, variant=v)
@@ -148,6 +183,7 @@ def cpu_reference_run(args, nparts, steps, warmup, target_seconds, chunk=0):
             variant = best[1]
         tb, ta = [], []
         label = None
+        t_start = time.time()
         for s in range(nsteps):
             t0 = time.time()
             rt = oracle.RefTree(x, y, z, m, max_leaf_n=args.max_leaf_n, ncrit=args.ncrit, variant=variant)
@@ -159,15 +195,14 @@ def cpu_reference_run(args, nparts, steps, warmup, target_seconds, chunk=0):
             if s >= warmup:
                 tb.append(t1 - t0)
                 ta.append(t2 - t1)
-            if sum(tb) + sum(ta) > target_seconds and len(ta) >= 1:
+            if time.time() - t_start > target_seconds and len(ta) >= 1:
                 break
         t_full = float(np.mean(tb) + np.mean(ta))
         sample = (f"{label}: full workload per step (construct octree {np.mean(tb):.3f} s + accs_u {np.mean(ta):.3f} s), "
-                  f"{len(ta)} timed steps, {cores} host threads; interactions/eval {i_total:.4g} from the oracle's "
-                  f"counters on every {cstride}-th critical node")
+                  f"{len(ta)} timed steps, {cores} host threads; interactions/eval {i_total:.6g}: {i_note}")
         return dict(value=i_total / t_full / 1e9, ms_per_step=t_full * 1e3, cores=cores, kind="reference",
                     sample=sample, traversal_ginter_s=i_total / float(np.mean(ta)) / 1e9, build_s=float(np.mean(tb)),
-                    interactions=i_total)
+                    interactions=i_total, timed_steps=len(ta))
     # ---- fallback: scalar oracle port, strided sample ----
     est_full = t_probe * cstride
     stride = max(1, int(np.ceil(est_full * nsteps / max(target_seconds, 1.0))))
@@ -180,13 +215,12 @@ def cpu_reference_run(args, nparts, steps, warmup, target_seconds, chunk=0):
             times.append(dt)
             inter.append(c["interactions"])
     rate = sum(inter) / sum(times)
-    i_total = float(np.mean(inter)) * stride
     t_full = t_obuild + i_total / rate
     sample = (f"oracle scalar port: full build once ({t_obuild:.2f} s, 1 thread) + traversal of every {stride}-th "
               f"critical node per step ({len(times)} timed steps, {cores} threads, {sum(times):.1f} s CPU wall); "
               f"extrapolated by interaction count")
     return dict(value=i_total / t_full / 1e9, ms_per_step=t_full * 1e3, cores=cores, kind="port", sample=sample,
-                traversal_ginter_s=rate / 1e9, build_s=t_obuild, interactions=i_total)
+                traversal_ginter_s=rate / 1e9, build_s=t_obuild, interactions=i_total, timed_steps=len(times))
 
 
 def run_reference(args):
@@ -194,47 +228,135 @@ def run_reference(args):
     if rank != 0:
         return
     # the arm's own workload: 4 M particles at N = 1, the 128 M strong-scaling workload (chunked generator) at N > 1,
-    # where the number of timed steps is bounded by wall clock (one evaluation takes ~15-20 s on 16 host cores)
+    # where one evaluation takes ~15 s on 16 host cores: the run is bounded by wall clock and reports the steps it
+    # actually timed
     big = args.gpus > 1 and not args.nparts
     nparts = args.nparts or (128_000_000 if big else 4_000_000)
-    r = cpu_reference_run(args, nparts, args.steps, min(args.warmup, 1) if big else args.warmup, 60.0 if big else 150.0,
+    r = cpu_reference_run(args, nparts, args.steps, min(args.warmup, 1) if big else args.warmup, 120.0 if big else 150.0,
                           chunk=(1 << 20) if args.gpus > 1 else 0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Ginteractions/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "steps": r["timed_steps"], "warmup": min(args.warmup, 1) if big else args.warmup,
+        "steps_requested": args.steps, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"plummer_{nparts}_fp32_theta{args.theta}_accs", "max_leaf_n": args.max_leaf_n,
-                   "ncrit": args.ncrit, "nparts": nparts},
+        "config": workload_config(args, nparts),
         "cpu_baseline": {"value": r["value"], "unit": "Ginteractions/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "Ginteractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
-
-
-def strong_scaling_base(nparts, ms_per_step):
-    """The same workload on ONE GPU, from the committed profile (the N = 1 line of this script measures the 4 M
-    headline workload, not this one): lets a reader form the strong-scaling speed-up on equal work."""
-    try:
-        path = os.path.join(ROOT, "profiles", "r01_bench_1gpu_128M_v7.json")
-        d = json.loads(open(path).read().strip().splitlines()[-1])
-        if int(d["config"]["nparts"]) != int(nparts):
-            return None
-        return {"n_gpus": 1, "ms_per_step": d["ms_per_step"], "value": d["value"], "source": os.path.relpath(path, ROOT),
-                "speedup_vs_1gpu": d["ms_per_step"] / ms_per_step}
-    except Exception:  # informational only
-        return None
+    if os.environ.get("RK_BENCH_PRINT_MAPS"):  # tests: the reference arm must not map the product library
+        libs = sorted({ln.split()[-1] for ln in open("/proc/self/maps") if ln.rstrip().endswith(".so")})
+        print("\n".join(libs), file=sys.stderr)
 
 
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
+def median(v):
+    return float(statistics.median(v))
+
+
+def kernel_traffic(kernel_name):
+    """DRAM bytes per launch of the traversal kernel from the committed ncu capture - only when that capture is of
+    the kernel variant this run launched."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traverse_kernel_latest.json")))
+        if prof.get("kernel") and prof["kernel"].split(" ")[0] == kernel_name.split(" ")[0]:
+            return prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
+def extras_single_gpu(args, rk, torch, dev, tree, dsh, nparts, fp32_peak, flush):
+    """Driver-visible measurements of BASELINE configs 2, 3, 4 and the one-GPU base of config 5 (N = 1 line)."""
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def timed_evals(t, src, Q, theta, G, eps, nsteps, n, outs):
+        ms, ks, info, bi = [], [], None, None
+        for s in range(nsteps + 1):
+            flush.zero_()
+            a, b = ev(), ev()
+            a.record()
+            bi = t.build(src[0], src[1], src[2], src[3], max_leaf_n=args.max_leaf_n, ncrit=args.ncrit,
+                         where=rk.RK_DEVICE, n=n)
+            t.acc_pot(Q, theta, G=G, eps=eps, out=outs, where=rk.RK_DEVICE)
+            b.record()
+            torch.cuda.synchronize()
+            if s:  # first = warm-up
+                ms.append(a.elapsed_time(b))
+                ks.append(t.eval_info.ms_kernel)
+            info = t.eval_info.asdict()
+        return median(ms), median(ks), info, bi.asdict()
+
+    # ---- config 2: same particles, accelerations + potentials, softening, G != 1 ----
+    outs = [torch.empty(nparts, dtype=torch.float32, device=dev) for _ in range(4)]
+    ms, k, info, _ = timed_evals(tree, dsh, 2, args.theta, 2.5, 0.01, 5, nparts, outs)
+    ach = (SLOTS_PER_INTERACTION + 1) * 2 * info["interactions"] / (k * 1e-3) / 1e12
+    out["config2_accs_pots_eps0.01_G2.5"] = {
+        "ms_per_step": ms, "ms_traverse_kernel": k, "ginteractions_per_s": info["interactions"] / (ms * 1e-3) / 1e9,
+        "interactions": info["interactions"], "kernel": tree.last_kernel(),
+        "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+                     "convention": "13 FP32 slots per interaction (accs + pots)"}}
+    del outs
+    # ---- config 3: fp64, theta = 0.5 ----
+    h64 = rk.plummer(nparts, fp=64)
+    d64 = [torch.from_numpy(a).to(dev) for a in (h64[1], h64[2], h64[3], h64[0])]
+    t64 = rk.Octree(fp=64, mac="bh", device=dev.index)
+    t64.set_stream(torch.cuda.current_stream().cuda_stream)
+    outs = [torch.empty(nparts, dtype=torch.float64, device=dev) for _ in range(3)]
+    ms, k, info, _ = timed_evals(t64, d64, 0, 0.5, 1.0, 0.0, 3, nparts, outs)
+    fp64_peak = rk.measure_fp64_peak(dev.index)
+    ach = SLOTS_PER_INTERACTION * 2 * info["interactions"] / (k * 1e-3) / 1e12
+    out["config3_fp64_theta0.5"] = {
+        "ms_per_step": ms, "ms_traverse_kernel": k, "ginteractions_per_s": info["interactions"] / (ms * 1e-3) / 1e9,
+        "interactions": info["interactions"], "kernel": t64.last_kernel(),
+        "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                     "convention": "12 FP64 slots per interaction counted as DFMA (2 flop) + the double rsqrt "
+                                   "(MUFU seed + Newton steps, not counted); peak = DFMA microbenchmark of this run"}}
+    t64.close()
+    del t64, d64, outs, h64
+    torch.cuda.empty_cache()
+    # ---- config 4: 16 M leapfrog (benchmark_leapfrog.cpp), device-resident and end to end ----
+    if hasattr(rk, "Leapfrog"):
+        try:
+            out["config4_leapfrog_16M"] = rk.leapfrog_benchmark(16_000_000, 10, theta=args.theta,
+                                                                max_leaf_n=args.max_leaf_n, ncrit=args.ncrit,
+                                                                device=dev.index)
+        except Exception as e:  # reported, never fatal for the headline line
+            out["config4_leapfrog_16M"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+    # ---- config 5, one GPU: the strong-scaling base, same chunked generator as the N > 1 runs ----
+    try:
+        nb = 128_000_000
+        t0 = time.time()
+        hb = rk.plummer(nb, 0, nb, fp=32, chunk=1 << 20)
+        tg = time.time() - t0
+        db = [torch.from_numpy(a).to(dev) for a in (hb[1], hb[2], hb[3], hb[0])]
+        del hb
+        outs = [torch.empty(nb, dtype=torch.float32, device=dev) for _ in range(3)]
+        ms, k, info, bi = timed_evals(tree, db, 0, args.theta, 1.0, 0.0, 2, nb, outs)
+        out["strong_scaling_base_128M"] = {
+            "n_gpus": 1, "nparts": nb, "ms_per_step": ms, "ms_build": bi["ms_total"], "ms_traverse_kernel": k,
+            "ginteractions_per_s": info["interactions"] / (ms * 1e-3) / 1e9, "interactions": info["interactions"],
+            "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"], "generator_s": tg,
+            "note": "same workload and generator as bench.py --gpus N > 1; divide by that run's ms_per_step for the "
+                    "strong-scaling speed-up on equal work"}
+        del db, outs
+    except Exception as e:
+        out["strong_scaling_base_128M"] = {"error": repr(e)}
+    tree.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import rakau_b200 as rk
-    from rakau_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -263,13 +385,12 @@ def run_ours(args):
 
     # resident copies of the shard (inputs in HBM when the timed region starts)
     dsh = [t.to(dev, non_blocking=True) for t in (hx, hy, hz, hm)]
-    counts = [max(0, min(nparts, min(r * per, nparts) + per) - min(r * per, nparts)) for r in range(world)]
     out_dev = [torch.zeros(nparts, dtype=torch.float32, device=dev) for _ in range(3)] if world == 1 else None
-    hout = [torch.empty(nparts, dtype=torch.float32).pin_memory() for _ in range(3)]
+    hout = [torch.empty(nparts if world == 1 else count, dtype=torch.float32).pin_memory() for _ in range(3)]
     hnp = [t.numpy() for t in (hx, hy, hz, hm)]
     hout_np = [t.numpy() for t in hout]
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
-    state = {"info": None, "bi": None, "imbalance": None, "d2h": 0}
+    state = {"info": None, "bi": None, "imbalance": None, "d2h": 0, "step": 0}
 
     sharded = None
     if world > 1:
@@ -278,6 +399,7 @@ def run_ours(args):
         tree = sharded.tree
 
     def step(e2e):
+        state["step"] += 1
         if world == 1 and e2e:
             # end to end through the C ABI with (pinned) HOST buffers: rk_tree_build copies the shard in,
             # rk_tree_acc_pot copies the accelerations out (pipelined with the traversal launches)
@@ -295,6 +417,10 @@ def run_ours(args):
             state["info"] = tree.eval_info.asdict()
             lo, hi = 0, nparts
         else:
+            if args.perturb:
+                # a small, deterministic displacement per step: the tree (and its critical nodes) changes
+                s = 1e-4 * (1 + state["step"] % 3)
+                src = [src[0] + s * src[1], src[1] - s * src[0], src[2], src[3]]
             # distributed sample sort + replicated topology, Morton-range sharded traversal, output exchange
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
@@ -304,10 +430,16 @@ def run_ours(args):
             state["info"], outs = sharded.acc_pot(0, args.theta)
             ev[2].record()
             state["phase_events"] = ev
+            state["outs"] = outs
             lo, hi = int(sharded.cut_particles[rank]), int(sharded.cut_particles[rank + 1])
         if e2e:
+            if world > 1 and hout[0].numel() < hi - lo:  # the cost-weighted range of this rank outgrew the buffers
+                hout[:] = [torch.empty(int((hi - lo) * 1.1), dtype=torch.float32).pin_memory() for _ in range(3)]
             for j in range(3):
-                hout[j][lo:hi].copy_(outs[j][lo:hi], non_blocking=True)  # each rank returns the slice it owns
+                if world == 1:
+                    hout[j][lo:hi].copy_(out_dev[j][lo:hi], non_blocking=True)
+                else:
+                    hout[j][:hi - lo].copy_(outs[j][lo:hi], non_blocking=True)  # each rank returns the slice it owns
             stream.synchronize()
         state["d2h"] = 12 * (hi - lo)
 
@@ -342,6 +474,9 @@ def run_ours(args):
     for w in range(max(args.warmup, 3)):
         step(False)
         refresh_costs()  # N > 1: cost-weighted cuts from the previous evaluation (converges in 2-3 steps)
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = sharded.check_against_single_gpu(dsh, first, args.theta, state["outs"], perturbed=args.perturb)
     step(True)
     fp32_peak = rk.measure_fp32_peak(local)
 
@@ -352,6 +487,7 @@ def run_ours(args):
     launches = rk.kernel_launch_count() - l0
     clk = clocks.stop()
     e2e_tot_ms, e2e_ms, _ = timed(args.steps, True)
+    kernel_name = tree.last_kernel()
 
     # whole-job interactions per step = sum over ranks
     inter = torch.tensor([infos[-1][0]["interactions"]], dtype=torch.float64, device=dev)
@@ -365,16 +501,10 @@ def run_ours(args):
     b_ms = float(np.mean([i[1]["ms_total"] for i in infos]))
     my_inter = infos[-1][0]["interactions"]
     achieved = SLOTS_PER_INTERACTION * 2 * my_inter / (k_ms * 1e-3) / 1e12  # FMA-equivalent TFLOP/s
-    traffic = None
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traverse_kernel_latest.json")))
-        traffic = prof.get("dram_bytes_per_launch")
-    except Exception:
-        pass
     bi = infos[-1][1]
-    # algorithmic build bytes (fp32, u64 codes), SURVEY §8(d): pack 16+16, encode 16+8, sort passes x (8 + 12 + 12),
-    # gather 4+16+16, perms 4+4+4, topology ~12, plus 64 B per node
-    build_bytes = nparts * (32 + 24 + bi["sort_passes"] * 32 + 36 + 12 + 12) + bi["n_nodes"] * 64
+    # algorithmic build bytes (fp32, u64 codes), SURVEY §8(d): pack 16+16, encode 16+8, one histogram pass 8,
+    # sort passes x (12 + 12), gather 4+16+16, perms 4+4+4, topology ~12, plus 64 B per node
+    build_bytes = nparts * (32 + 24 + 8 + bi["sort_passes"] * 24 + 36 + 12 + 12) + bi["n_nodes"] * 64
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -385,15 +515,15 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "Ginteractions/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"plummer_{nparts}_fp32_theta{args.theta}_accs", "nparts": nparts,
-                   "max_leaf_n": args.max_leaf_n, "ncrit": args.ncrit, "mac": "bh", "G": 1.0, "eps": 0.0,
-                   "parallelism": (f"sample_sort_build+morton_range_traversal_x{world}" if world > 1 else "single_gpu"),
-                   "l2": "256 MiB buffer written between timed iterations", "interactions_per_step": inter,
-                   "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"], "shard_cost_imbalance": state["imbalance"]},
+        "config": workload_config(args, nparts),
+        "tree": {"interactions_per_step": inter, "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"],
+                 "sharding": (f"sample_sort_build+morton_range_traversal_x{world}" if world > 1 else "single_gpu"),
+                 "shard_cost_imbalance": state["imbalance"]},
         "ms_build": b_ms, "ms_traverse_kernel": k_ms,
         "build_phases_ms": {k: bi[k] for k in ("ms_encode", "ms_sort", "ms_permute", "ms_topology", "ms_props")},
-        "roofline": {"bound": "fp32", "kernel": "traverse_kernel<float,0,0,64>", "achieved": achieved,
-                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
+        "roofline": {"bound": "fp32", "kernel": kernel_name, "achieved": achieved,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                     "traffic": kernel_traffic(kernel_name),
                      "convention": "12 FP32 issue slots per interaction counted as FMA (2 flop); peak = FFMA "
                                    "microbenchmark measured in this run",
                      "gflops_literature_20flop": FLOP_PER_INTERACTION_LIT * my_inter / (k_ms * 1e-3) / 1e9},
@@ -421,9 +551,16 @@ def run_ours(args):
         kall = [torch.zeros_like(km) for _ in range(world)]
         dist.all_gather(kall, km)
         line["ms_traverse_kernel_per_rank"] = [float(k.item()) for k in kall]
-        line["build_note"] = ("ms_build = distributed sample sort (local sort, all-to-all, bucket sort, all-gather) + "
+        line["build_note"] = ("ms_build = distributed sample sort (local sort, bucket exchange, bucket sort, gather) + "
                               "replicated topology/properties; build_phases_ms covers the replicated part only")
-        line["strong_scaling_base"] = strong_scaling_base(nparts, ms_per_step)
+        line["parity_checked"] = bool(parity and parity.get("ok"))
+        line["parity"] = parity
+        line["perturbed_between_steps"] = bool(args.perturb)
+    if world == 1 and not args.no_extras and not args.nparts:
+        try:
+            line["configs"] = extras_single_gpu(args, rk, torch, dev, tree, dsh, nparts, fp32_peak, flush)
+        except Exception as e:  # the headline line must survive a failure of the additional blocks
+            line["configs"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             r = cpu_reference_run(args, nparts, 4, 1, args.cpu_seconds)

@@ -451,6 +451,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
     constexpr u32 NONE = 0xffffffffu;
     const u32 ksteal = (RK_STEAL && p.steal && W) ? (p.steal_k < n_units ? p.steal_k : n_units) : 0u;
     bool queue_empty = false;
+    // every warp scans the published runs from its own position (no herd on the first run with work left)
+    u32 scan_pos = (blockIdx.x * u32(TRAV_WARPS) + u32(warp)) * 97u, backoff = 1000u;
 
     for (;;) {
         // ---- attach to a run: the next unit of the queue, or a published run of the last wave ----
@@ -514,21 +516,27 @@ __global__ void __launch_bounds__(TRAV_THREADS, RK_CTAS) traverse_kernel(const t
             for (;;) {
                 const u32 pub = *static_cast<volatile u32 *>(p.steal_published); // read BEFORE the scan
                 for (u32 sb = 0; sb < ksteal && slot == NONE; sb += 32u) {
-                    const u32 si = sb + static_cast<u32>(lane);
+                    const u32 si = (scan_pos + sb + static_cast<u32>(lane)) % ksteal;
                     bool ok = false;
-                    if (si < ksteal) {
+                    if (sb + static_cast<u32>(lane) < ksteal) {
                         const volatile u32 *h = p.steal + size_t(si) * 16u;
                         ok = h[2] != 0u && h[0] < h[1];
                     }
                     const u32 m = __ballot_sync(FULL, ok);
                     if (m) {
-                        slot = sb + static_cast<u32>(__ffs(m)) - 1u;
+                        slot = __shfl_sync(FULL, si, __ffs(m) - 1);
                     }
                 }
-                if (slot != NONE || pub == ksteal) {
-                    break; // (pub == ksteal: every run of the last wave was resolved before the scan, none has work left)
+                if (slot != NONE) {
+                    scan_pos = slot;
+                    backoff = 1000u;
+                    break;
                 }
-                __nanosleep(500);
+                if (pub == ksteal) {
+                    break; // every run of the last wave was resolved before the scan and none has work left
+                }
+                __nanosleep(backoff);
+                backoff = backoff < 8000u ? backoff * 2u : backoff;
             }
             if (slot == NONE) {
                 break;

@@ -10,8 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line(rk):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--nparts", "200000",
-                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, RK_BENCH_PRINT_MAPS="1"))
     assert r.returncode == 0, r.stderr[-2000:]
+    assert "librakau_b200" not in r.stderr and "liboracle" in r.stderr  # the arm maps the checker, never the product
     lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
@@ -23,6 +25,13 @@ def test_reference_arm_prints_the_contract_line(rk):
     assert d["cpu_baseline"]["value"] == d["value"] and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "Ginteractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "plummer_200000_fp32_theta0.75_accs"
+    assert d["steps"] == 1 and d["steps_requested"] == 1  # the steps actually timed
+    # both arms describe the workload with the same keys and values
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    ns = argparse.Namespace(gpus=1, nparts=200000, theta=0.75, max_leaf_n=16, ncrit=128)
+    assert d["config"] == bench.workload_config(ns, 200000)
 
 
 def test_reference_arm_other_ranks_exit_without_work(rk):
