@@ -293,33 +293,42 @@ def extras_single_gpu(args, rk, torch, dev, tree, dsh, nparts, fp32_peak, flush)
         return median(ms), median(ks), info, bi.asdict()
 
     # ---- config 2: same particles, accelerations + potentials, softening, G != 1 ----
-    outs = [torch.empty(nparts, dtype=torch.float32, device=dev) for _ in range(4)]
-    ms, k, info, _ = timed_evals(tree, dsh, 2, args.theta, 2.5, 0.01, 5, nparts, outs)
-    ach = (SLOTS_PER_INTERACTION + 1) * 2 * info["interactions"] / (k * 1e-3) / 1e12
-    out["config2_accs_pots_eps0.01_G2.5"] = {
-        "ms_per_step": ms, "ms_traverse_kernel": k, "ginteractions_per_s": info["interactions"] / (ms * 1e-3) / 1e9,
-        "interactions": info["interactions"], "kernel": tree.last_kernel(),
-        "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-                     "convention": "13 FP32 slots per interaction (accs + pots)"}}
-    del outs
+    def config2():
+        outs = [torch.empty(nparts, dtype=torch.float32, device=dev) for _ in range(4)]
+        ms, k, info, _ = timed_evals(tree, dsh, 2, args.theta, 2.5, 0.01, 5, nparts, outs)
+        ach = (SLOTS_PER_INTERACTION + 1) * 2 * info["interactions"] / (k * 1e-3) / 1e12
+        return {"ms_per_step": ms, "ms_traverse_kernel": k,
+                "ginteractions_per_s": info["interactions"] / (ms * 1e-3) / 1e9,
+                "interactions": info["interactions"], "kernel": tree.last_kernel(),
+                "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                             "frac": ach / fp32_peak, "convention": "13 FP32 slots per interaction (accs + pots)"}}
+
     # ---- config 3: fp64, theta = 0.5 ----
-    h64 = rk.plummer(nparts, fp=64)
-    d64 = [torch.from_numpy(a).to(dev) for a in (h64[1], h64[2], h64[3], h64[0])]
-    t64 = rk.Octree(fp=64, mac="bh", device=dev.index)
-    t64.set_stream(torch.cuda.current_stream().cuda_stream)
-    outs = [torch.empty(nparts, dtype=torch.float64, device=dev) for _ in range(3)]
-    ms, k, info, _ = timed_evals(t64, d64, 0, 0.5, 1.0, 0.0, 3, nparts, outs)
-    fp64_peak = rk.measure_fp64_peak(dev.index)
-    ach = SLOTS_PER_INTERACTION * 2 * info["interactions"] / (k * 1e-3) / 1e12
-    out["config3_fp64_theta0.5"] = {
-        "ms_per_step": ms, "ms_traverse_kernel": k, "ginteractions_per_s": info["interactions"] / (ms * 1e-3) / 1e9,
-        "interactions": info["interactions"], "kernel": t64.last_kernel(),
-        "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                     "convention": "12 FP64 slots per interaction counted as DFMA (2 flop) + the double rsqrt "
-                                   "(MUFU seed + Newton steps, not counted); peak = DFMA microbenchmark of this run"}}
-    t64.close()
-    del t64, d64, outs, h64
-    torch.cuda.empty_cache()
+    def config3():
+        h64 = rk.plummer(nparts, fp=64)
+        d64 = [torch.from_numpy(a).to(dev) for a in (h64[1], h64[2], h64[3], h64[0])]
+        t64 = rk.Octree(fp=64, mac="bh", device=dev.index)
+        t64.set_stream(torch.cuda.current_stream().cuda_stream)
+        outs = [torch.empty(nparts, dtype=torch.float64, device=dev) for _ in range(3)]
+        ms, k, info, _ = timed_evals(t64, d64, 0, 0.5, 1.0, 0.0, 3, nparts, outs)
+        fp64_peak = rk.measure_fp64_peak(dev.index)
+        ach = SLOTS_PER_INTERACTION * 2 * info["interactions"] / (k * 1e-3) / 1e12
+        res = {"ms_per_step": ms, "ms_traverse_kernel": k,
+               "ginteractions_per_s": info["interactions"] / (ms * 1e-3) / 1e9,
+               "interactions": info["interactions"], "kernel": t64.last_kernel(),
+               "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": ach / fp64_peak,
+                            "convention": "12 FP64 slots per interaction counted as DFMA (2 flop) + the double rsqrt "
+                                          "(not counted); peak = DFMA microbenchmark of this run"}}
+        t64.close()
+        return res
+
+    for name, fn in (("config2_accs_pots_eps0.01_G2.5", config2), ("config3_fp64_theta0.5", config3)):
+        try:
+            out[name] = fn()
+        except Exception as e:  # each block is reported on its own
+            out[name] = {"error": repr(e)}
+        torch.cuda.empty_cache()
     # ---- config 4: 16 M leapfrog (benchmark_leapfrog.cpp), device-resident and end to end ----
     if hasattr(rk, "Leapfrog"):
         try:
@@ -348,7 +357,6 @@ def extras_single_gpu(args, rk, torch, dev, tree, dsh, nparts, fp32_peak, flush)
         del db, outs
     except Exception as e:
         out["strong_scaling_base_128M"] = {"error": repr(e)}
-    tree.clear()
     torch.cuda.empty_cache()
     return out
 
@@ -476,7 +484,10 @@ def run_ours(args):
         refresh_costs()  # N > 1: cost-weighted cuts from the previous evaluation (converges in 2-3 steps)
     parity = None
     if world > 1 and not args.no_parity_check:
-        parity = sharded.check_against_single_gpu(dsh, first, args.theta, state["outs"], perturbed=args.perturb)
+        perturb, args.perturb = args.perturb, False
+        step(False)  # (an unperturbed evaluation of the resident shard, compared with a single-GPU one)
+        args.perturb = perturb
+        parity = sharded.check_against_single_gpu(dsh, first, args.theta, state["outs"])
     step(True)
     fp32_peak = rk.measure_fp32_peak(local)
 

@@ -212,6 +212,9 @@ class Octree:
         m = self._prep(m, where)
         self._check(self.L.rk_tree_update_masses(self.h, _ptr(m), where))
 
+    def clear(self):
+        self._check(self.L.rk_tree_clear(self.h))
+
     @property
     def nparts(self):
         return self.L.rk_tree_nparts(self.h)

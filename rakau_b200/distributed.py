@@ -37,11 +37,17 @@ class ShardedTree:
                 t.set_stream(s)
         self.nsamp = samples_per_rank
         self._bufs = {}
-        self.cuts = None
+        self.cuts = None           # critical-node index where every rank's range starts (world + 1 entries)
         self.cut_particles = None  # first particle of every rank's range
+        # The cuts are remembered as PARTICLE indices: a rebuild with moved particles changes the critical nodes, so
+        # the cost-weighted boundaries are re-snapped to the new critical nodes (as tree.hpp:3168-3178 snaps the
+        # reference's split) instead of being thrown away.
+        self.cut_pidx = None
+        self._build_id, self._cuts_build_id = 0, -1
         self._side = None  # stream of the particle all-gather that runs underneath the topology build
         self._push = None  # per-peer copy streams of the output exchange
-        self._peer = None  # (capacity, buffers, per-buffer list of every rank's device pointer) or False
+        self._peer = None  # two sets of (capacity, buffers, per-buffer list of every rank's device pointer), or False
+        self._peer_flip = 0
 
     # ---- build -------------------------------------------------------------------------------------------
     def build(self, x, y, z, m, first_index):
@@ -136,6 +142,7 @@ class ShardedTree:
             main.wait_stream(self._side)
         self._ev.append(('topology_props_and_particle_gather', self._rec()))
         self.cut_particles = None
+        self._build_id += 1
         return bi_
 
     def _rec(self):
@@ -193,38 +200,53 @@ class ShardedTree:
         return full
 
     # ---- traversal -----------------------------------------------------------------------------------------
+    def _snap(self, pidx):
+        """Critical-node cuts for the given particle boundaries (first critical node starting at or after each)."""
+        inner = [int(v) for v in pidx[1:-1]]
+        cuts = []
+        for i in range(0, len(inner), 16):  # rk_tree_crit_lower_bound takes 16 values per call
+            cuts += [int(v) for v in self.tree.crit_lower_bound(inner[i:i + 16])]
+        return [0] + cuts + [int(self.tree.ncrit_nodes)]
+
     def _ensure_cuts(self):
-        C = self.tree.ncrit_nodes
-        if self.cuts is None or self.cuts[-1] != C:
-            # first evaluation of this tree shape: equal particle counts (tree.hpp:3147-3178)
-            cr = self.tree.crit()[:, 1].astype(np.int64)
-            self.cuts = sharding.cuts_by_particles(cr, self.n, self.world)
-            self.cut_particles = None
-        if self.cut_particles is None:
+        if self.cut_pidx is None or int(self.cut_pidx[-1]) != self.n or len(self.cut_pidx) != self.world + 1:
+            # first evaluation: equal particle counts (tree.hpp:3147-3178)
+            self.cut_pidx = [(r * self.n) // self.world for r in range(self.world)] + [self.n]
+            self._cuts_build_id = -1
+        if self._cuts_build_id != self._build_id:
+            self.cuts = self._snap(self.cut_pidx)
             self.cut_particles = self.tree.crit_begin_at(self.cuts).astype(np.int64)
+            self._cuts_build_id = self._build_id
 
     def _peer_outputs(self, nres):
         """Result buffers in CUDA peer memory (torch symmetric memory: every rank maps every other rank's buffer),
         allocated once for n particles. None if the platform cannot provide it (then NCCL does the exchange)."""
         if self._peer is False:
             return None
-        if self._peer is not None and self._peer[0] >= self.n and len(self._peer[1]) >= nres:
-            return self._peer
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-            cap = int(self.n * 1.02) + 16
-            bufs, ptrs = [], []
-            for _ in range(max(nres, 3)):
-                t = symm_mem.empty(cap, dtype=self.dt, device=self.dev)
-                h = symm_mem.rendezvous(t, self.dist.group.WORLD)
-                bufs.append(t)
-                ptrs.append([int(p) for p in h.buffer_ptrs])
-            self._peer = (cap, bufs, ptrs)
-        except Exception as exc:  # noqa: BLE001 - no peer memory on this platform: use the collective path
-            self._peer = False
-            self._peer_error = repr(exc)
-            return None
-        return self._peer
+        if self._peer is None or self._peer[0][0] < self.n or len(self._peer[0][1]) < nres:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                cap = int(self.n * 1.02) + 16
+                sets = []
+                for _ in range(2):
+                    bufs, ptrs = [], []
+                    for _ in range(max(nres, 3)):
+                        t = symm_mem.empty(cap, dtype=self.dt, device=self.dev)
+                        h = symm_mem.rendezvous(t, self.dist.group.WORLD)
+                        bufs.append(t)
+                        ptrs.append([int(p) for p in h.buffer_ptrs])
+                    sets.append((cap, bufs, ptrs))
+                self._peer = sets
+            except Exception as exc:  # noqa: BLE001 - no peer memory on this platform: use the collective path
+                self._peer = False
+                self._peer_error = repr(exc)
+                return None
+        # Two sets, alternating between evaluations: a fast rank pushes the slices of evaluation k+1 into set B while a
+        # slow peer's kernels may still read the results of evaluation k in set A. Set A is written again by
+        # evaluation k+2, whose pushes start after the barrier that ends evaluation k+1 - and every rank enters that
+        # barrier in stream order behind its readers of set A.
+        self._peer_flip ^= 1
+        return self._peer[self._peer_flip]
 
     def acc_pot(self, Q, theta, out=None, G=1.0, eps=0.0, exchange=True, chunks=(0.4, 0.7, 0.9)):
         """Evaluate this rank's Morton range; with exchange=True every rank ends with the full result (Morton order).
@@ -277,6 +299,9 @@ class ShardedTree:
             s.wait_stream(main)
         esz = out[0].element_size()
         info = None
+        if len(ccuts) < 2:  # an empty range (more ranks than critical nodes): nothing to evaluate, still exchange
+            from . import EvalInfo
+            info = EvalInfo().asdict()
         for k in range(len(ccuts) - 1):
             self.tree.acc_pot(Q, theta, G=G, eps=eps, out=out, where=RK_DEVICE, crit_range=(ccuts[k], ccuts[k + 1]))
             part = self.tree.eval_info.asdict()  # (the call returns after its launch has finished)
@@ -316,5 +341,47 @@ class ShardedTree:
         self.dist.all_reduce(t)
         costs = t.cpu().numpy()
         self.cuts = sharding.cuts_by_cost(costs, self.world)
-        self.cut_particles = None
+        self.cut_particles = self.tree.crit_begin_at(self.cuts).astype(np.int64)
+        self.cut_pidx = [int(v) for v in self.cut_particles]  # survives the next rebuild (re-snapped in _ensure_cuts)
+        self._cuts_build_id = self._build_id
         return sharding.imbalance(costs, self.cuts)
+
+    def check_against_single_gpu(self, shard, first_index, theta, outs, G=1.0, eps=0.0):
+        """Hardware parity of the sharded path: every rank gathers the whole input, builds the single-GPU tree and
+        evaluates ALL critical nodes with it, then compares (1) the fingerprints of the two trees' device arrays
+        (codes, permutation, particles, node topology and properties, critical nodes: rk_tree_digest) and (2) the
+        accelerations the sharded evaluation left on this rank, bit for bit. shard: this rank's x, y, z, m of the
+        last build; outs: the outputs of the last acc_pot (Morton order, complete on every rank)."""
+        torch, dist = self.torch, self.dist
+        n_loc = shard[0].numel()
+        sizes = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([n_loc], dtype=torch.int64, device=self.dev))
+        sizes = [int(v) for v in sizes.tolist()]
+        mx = max(sizes)
+        full = []
+        for t in shard:
+            pad = torch.zeros(mx, dtype=t.dtype, device=self.dev)
+            pad[:n_loc] = t
+            allb = torch.empty(mx * self.world, dtype=t.dtype, device=self.dev)
+            dist.all_gather_into_tensor(allb, pad)
+            full.append(torch.cat([allb[r * mx:r * mx + sizes[r]] for r in range(self.world)]))
+            del pad, allb
+        n = full[0].numel()
+        single = Octree(fp=self.fp, mac="bh" if self.tree.mac == 0 else "bh_geom", device=self.dev.index)
+        single.set_stream(torch.cuda.current_stream().cuda_stream)
+        single.build(full[0], full[1], full[2], full[3], max_leaf_n=self.mln, ncrit=self.ncrit, where=RK_DEVICE, n=n)
+        d1, d2 = single.digest(), self.tree.digest()
+        names = ("codes", "perm", "particles", "node_topology", "node_properties", "crit_nodes", "crit_begins", "sizes")
+        differing = [nm for nm, a, b in zip(names, d1, d2) if int(a) != int(b)]
+        ref = [torch.empty(n, dtype=self.dt, device=self.dev) for _ in range(len(outs))]
+        Q = {3: 0, 1: 1, 4: 2}[len(outs)]
+        single.acc_pot(Q, theta, G=G, eps=eps, out=ref, where=RK_DEVICE)
+        acc_equal = all(bool(torch.equal(a[:n], b)) for a, b in zip(outs, ref))
+        max_diff = max(float((a[:n] - b).abs().max().item()) for a, b in zip(outs, ref))
+        ok = torch.tensor([1 if (not differing and acc_equal) else 0], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        single.close()
+        return {"ok": bool(ok.item()), "nparts": n, "tree_arrays_differing": differing,
+                "accelerations_bit_equal": acc_equal, "max_abs_diff": max_diff,
+                "what": "sharded tree fingerprints and gathered accelerations vs a single-GPU build + full evaluation "
+                        "of the same particles on every rank"}

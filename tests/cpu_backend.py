@@ -63,7 +63,10 @@ class CpuOctree:
         self._parts = [self._np(a)[:n].copy() for a in (x, y, z, m)]
         self._perm = self._np(perm)[:n].copy()
         self.n = n
-        self._begin = np.arange(0, n, ncrit, dtype=np.int64)
+        # blocks of ncrit particles, shifted by a build counter so that a REBUILD changes the critical nodes
+        self._nbuilds = getattr(self, "_nbuilds", 0) + 1
+        first = (17 * (self._nbuilds - 1)) % ncrit
+        self._begin = np.unique(np.concatenate([[0], np.arange(first, n, ncrit, dtype=np.int64)]))
         self._costs = np.zeros(self._begin.size, dtype=np.uint64)
         return _Info(n_nodes=int(self._begin.size), n_crit=int(self._begin.size), box_size=float(box_size))
 
@@ -78,6 +81,9 @@ class CpuOctree:
     def crit_begin_at(self, idx):
         b = np.append(self._begin, self.n)
         return b[np.asarray(idx, dtype=np.int64)].astype(np.uint64)
+
+    def crit_lower_bound(self, particle_idx):
+        return np.searchsorted(self._begin, np.asarray(particle_idx, dtype=np.int64), side="left").astype(np.uint64)
 
     @staticmethod
     def expected(parts, j):

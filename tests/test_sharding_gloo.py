@@ -99,9 +99,18 @@ def _sharded_worker(rank, world, port, q):
     sorted_parts = [a[p] for a in full]
     ok_eval = all(bool((o.numpy()[:N] == CpuOctree.expected(sorted_parts, j)).all()) for j, o in enumerate(out1))
     ok_eval &= all(bool((o.numpy() == CpuOctree.expected(sorted_parts, j)).all()) for j, o in enumerate(out2))
+    # a rebuild changes the critical nodes: the cost-weighted cuts must survive as particle boundaries, re-snapped to
+    # the new critical nodes (not fall back to equal particle counts)
+    pidx2 = [int(v) for v in st.cut_particles]
+    st.build(*shard, first_index=first)
+    info3, out3 = st.acc_pot(0, 0.75, out=[torch.full((N,), float("nan")) for _ in range(3)])
+    begins = np.append(st.tree._begin, N)
+    ok_resnap = all(int(begins[c]) >= pb and (c == 0 or int(begins[c - 1]) < pb) for c, pb in zip(st.cuts[1:-1], pidx2[1:-1]))
+    ok_resnap &= [int(v) for v in st.cut_pidx] == pidx2
+    ok_eval &= all(bool((o.numpy() == CpuOctree.expected(sorted_parts, j)).all()) for j, o in enumerate(out3))
     tot = torch.tensor([info1["interactions"], info2["interactions"]], dtype=torch.int64)
     dist.all_reduce(tot)
-    q.put((rank, ok_build, ok_eval, cuts1, cuts2, imb, tot.tolist()))
+    q.put((rank, ok_build, ok_eval and ok_resnap, cuts1, cuts2, imb, tot.tolist()))
     dist.destroy_process_group()
 
 
