@@ -223,6 +223,30 @@ def cpu_reference_run(args, nparts, steps, warmup, target_seconds, chunk=0):
                 traversal_ginter_s=rate / 1e9, build_s=t_obuild, interactions=i_total, timed_steps=len(times))
 
 
+def reference_cuda_run(args, nparts, reps=3):
+    """Second baseline (north_star: "next to the reference's own CUDA backend if it builds offline"): the unmodified
+    reference header with RAKAU_WITH_CUDA and its own src/rakau_cuda.cu compiled for sm_100a (oracle/_ref/libref_cuda.so),
+    driven through the reference's public API: accs_u(..., split = {0, 1}) = everything on its GPU path. The tree is
+    built by the reference on the CPU (not timed here); every call uploads tree + particles and downloads the results
+    (stateless by design, rakau_cuda.cu:348-528), which its own timer includes as well (tree.hpp:3297)."""
+    import oracle  # noqa: test infrastructure
+    if not oracle.ref_available("cuda"):
+        return {"unavailable": "oracle/_ref/libref_cuda.so was not built"}
+    m, x, y, z = oracle.plummer(nparts)
+    t0 = time.time()
+    rt = oracle.RefTree(x, y, z, m, max_leaf_n=args.max_leaf_n, ncrit=args.ncrit, variant="cuda")
+    t_build = time.time() - t0
+    ts = []
+    for _ in range(reps + 1):
+        t0 = time.time()
+        rt.acc_pot(0, args.theta, split=[0.0, 1.0])
+        ts.append(time.time() - t0)
+    return {"what": rt.variant(), "ms_per_accs_u_call": 1e3 * float(np.median(ts[1:])), "calls": reps,
+            "cpu_tree_build_ms_not_included": 1e3 * t_build,
+            "note": "per-particle MAC and traversal (rakau_cuda.cu:152-335), host-to-device copy of tree and particles "
+                    "and device-to-host copy of the results inside every call; README V100 figure for this workload: 95 ms"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -580,6 +604,11 @@ def run_ours(args):
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {e}"}
+        try:
+            line["reference_cuda_backend"] = reference_cuda_run(args, nparts)
+            line["reference_cuda_backend"]["ours_same_call_ms"] = line["e2e"]["ms_per_step"]
+        except Exception as e:
+            line["reference_cuda_backend"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -280,6 +280,8 @@ def ref_lib(variant="scalar"):
     L.ref_get_nodes.argtypes = [vp, vp]
     L.ref_acc_pot.restype = i32
     L.ref_acc_pot.argtypes = [vp, i32, dbl, dbl, dbl, vp, vp, vp, vp]
+    L.ref_acc_pot_split.restype = i32
+    L.ref_acc_pot_split.argtypes = [vp, i32, dbl, dbl, dbl, vp, vp, vp, vp, vp, sz]
     L.ref_exact.restype = i32
     L.ref_exact.argtypes = [vp, sz, dbl, dbl, vp]
     L.ref_update_positions.restype = i32
@@ -344,11 +346,18 @@ class RefTree:
         self.L.ref_get_nodes(self.h, _p(out))
         return out
 
-    def acc_pot(self, Q, theta, G=1.0, eps=0.0):
+    def acc_pot(self, Q, theta, G=1.0, eps=0.0, split=None):
+        """split: the reference's `split` kwarg (tree.hpp:3147-3198; CPU share first, then one share per accelerator).
+        Only the variants built with RAKAU_WITH_CUDA ("bridge": cuda_acc_pot_impl = integration/rakau_b200_bridge.cpp,
+        "cuda": the reference's own src/rakau_cuda.cu) accept more than one entry."""
         nres = {0: 3, 1: 1, 2: 4}[Q]
         out = [np.zeros(self.nparts, dtype=self.F) for _ in range(nres)]
         ptrs = [_p(a) for a in out] + [None] * (4 - nres)
-        rc = self.L.ref_acc_pot(self.h, Q, float(theta), float(G), float(eps), *ptrs)
+        if split is not None:
+            sp = np.ascontiguousarray(split, dtype=np.float64)
+            rc = self.L.ref_acc_pot_split(self.h, Q, float(theta), float(G), float(eps), *ptrs, _p(sp), sp.size)
+        else:
+            rc = self.L.ref_acc_pot(self.h, Q, float(theta), float(G), float(eps), *ptrs)
         if rc:
             raise OracleError(rc, self.L.ref_last_error(self.h).decode())
         return out

@@ -29,7 +29,8 @@ struct iface {
     virtual void perm(int which, std::uint64_t *) const = 0;
     virtual void parts(void *x, void *y, void *z, void *m) const = 0;
     virtual void nodes(void *out) const = 0; // {u64 begin,end,n_children,code,level; F props[4]; F dim; F delta}
-    virtual void acc_pot(int Q, double theta, double G, double eps, void *o0, void *o1, void *o2, void *o3) const = 0;
+    virtual void acc_pot(int Q, double theta, double G, double eps, void *o0, void *o1, void *o2, void *o3,
+                         const std::vector<double> &split) const = 0;
     virtual void exact(std::size_t idx, double G, double eps, double *out4) const = 0;
     virtual void update_positions(const void *x, const void *y, const void *z) = 0;
     virtual void update_masses(const void *m) = 0;
@@ -90,17 +91,19 @@ struct impl final : iface {
             ++i;
         }
     }
-    void acc_pot(int Q, double theta, double Gc, double e, void *o0, void *o1, void *o2, void *o3) const override
+    void acc_pot(int Q, double theta, double Gc, double e, void *o0, void *o1, void *o2, void *o3,
+                 const std::vector<double> &sp) const override
     {
+        // (split = {}: the reference's default, everything on the CPU)
         if (Q == 0) {
             t.accs_u(std::array<F *, 3>{static_cast<F *>(o0), static_cast<F *>(o1), static_cast<F *>(o2)}, F(theta),
-                     G = F(Gc), eps = F(e));
+                     G = F(Gc), eps = F(e), split = sp);
         } else if (Q == 1) {
-            t.pots_u(static_cast<F *>(o0), F(theta), G = F(Gc), eps = F(e));
+            t.pots_u(static_cast<F *>(o0), F(theta), G = F(Gc), eps = F(e), split = sp);
         } else {
             t.accs_pots_u(std::array<F *, 4>{static_cast<F *>(o0), static_cast<F *>(o1), static_cast<F *>(o2),
                                              static_cast<F *>(o3)},
-                          F(theta), G = F(Gc), eps = F(e));
+                          F(theta), G = F(Gc), eps = F(e), split = sp);
         }
     }
     void exact(std::size_t idx, double Gc, double e, double *out4) const override
@@ -140,7 +143,11 @@ struct handle {
 
 REF_API const char *ref_variant()
 {
-#if defined(RAKAU_DISABLE_SIMD)
+#if defined(RAKAU_SHIM_BRIDGE)
+    return "reference source, shimmed deps, RAKAU_WITH_CUDA: cuda_acc_pot_impl = integration/rakau_b200_bridge.cpp";
+#elif defined(RAKAU_WITH_CUDA)
+    return "reference source, shimmed deps, RAKAU_WITH_CUDA: the reference's own src/rakau_cuda.cu (nvcc, sm_100a)";
+#elif defined(RAKAU_DISABLE_SIMD)
     return "reference source, shimmed deps, scalar (RAKAU_DISABLE_SIMD), stable sort";
 #elif defined(__AVX512F__)
     return "reference source, shimmed deps (OpenMP-backed TBB stand-in), AVX-512 batches + rsqrt14";
@@ -223,7 +230,15 @@ static int guarded(void *p, Fn &&fn)
 }
 REF_API int ref_acc_pot(void *p, int Q, double theta, double G, double eps, void *o0, void *o1, void *o2, void *o3)
 {
-    return guarded(p, [&]() { static_cast<handle *>(p)->p->acc_pot(Q, theta, G, eps, o0, o1, o2, o3); });
+    return guarded(p, [&]() { static_cast<handle *>(p)->p->acc_pot(Q, theta, G, eps, o0, o1, o2, o3, {}); });
+}
+// The reference's `split` kwarg (tree.hpp:3147-3198): split[0] = CPU share, split[1..] = accelerator shares.
+REF_API int ref_acc_pot_split(void *p, int Q, double theta, double G, double eps, void *o0, void *o1, void *o2,
+                              void *o3, const double *split, std::size_t nsplit)
+{
+    return guarded(p, [&]() {
+        static_cast<handle *>(p)->p->acc_pot(Q, theta, G, eps, o0, o1, o2, o3, std::vector<double>(split, split + nsplit));
+    });
 }
 REF_API int ref_exact(void *p, std::size_t idx, double G, double eps, double *out4)
 {
