@@ -102,6 +102,9 @@ RK_API const char *rk_create_error(void);
  * non-blocking stream. */
 RK_API int rk_tree_set_stream(rk_tree *t, void *cuda_stream);
 RK_API int rk_tree_synchronize(rk_tree *t);
+/* Tuning switches that never change results beyond the documented tolerances. "props_bottom_up": node properties
+ * bottom-up (1: every particle read once, one launch per level), top-down (0) or chosen by size (-1, the default). */
+RK_API int rk_tree_set_option(rk_tree *t, const char *name, long long value);
 
 /* ---- construction: construct_impl, tree.hpp:1329-1487 ------------------------------------------------ */
 /* Copies n particles (SoA x, y, z, m; host or device pointers) into the tree, deduces the box if

@@ -35,7 +35,7 @@ SYMBOLS = [
     "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak", "rk_device_copy_async",
     "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
     "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
-    "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak",
+    "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak", "rk_tree_set_option",
 ]
 
 
@@ -123,6 +123,7 @@ def lib():
     L.rk_tree_crit_begin_at.argtypes = [vp, vp, sz, vp]
     L.rk_tree_crit_lower_bound.argtypes = [vp, vp, sz, vp]
     L.rk_tree_digest.argtypes = [vp, vp]
+    L.rk_tree_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     L.rk_tree_last_kernel.restype = C.c_char_p
     L.rk_tree_last_kernel.argtypes = [vp]
     L.rk_measure_fp64_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
@@ -186,6 +187,9 @@ class Octree:
 
     def synchronize(self):
         self._check(self.L.rk_tree_synchronize(self.h))
+
+    def set_option(self, name, value):
+        self._check(self.L.rk_tree_set_option(self.h, name.encode(), int(value)))
 
     def build(self, x, y, z, m, box_size=0.0, max_leaf_n=16, ncrit=128, where=RK_HOST, n=None):
         arrs = [self._prep(a, where) for a in (x, y, z, m)]

@@ -980,6 +980,14 @@ public:
     }
 
     const char *last_kernel() const { return m_kernel_name; }
+    void set_option(const std::string &name, long long value)
+    {
+        if (name == "props_bottom_up") {
+            m_b.props_bottom_up = value < 0 ? -1 : (value != 0);
+        } else {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_set_option: unknown option '" + name + "'");
+        }
+    }
     // Order-independent fingerprints of the device arrays (multi-GPU parity checks without moving the tree to the host).
     void digest(uint64_t out[8])
     {
@@ -1581,6 +1589,10 @@ const void *rk_tree_group_costs_device(rk_tree *t)
     return t->fp == 32 ? t->t32->group_costs_device() : t->t64->group_costs_device();
 }
 
+int rk_tree_set_option(rk_tree *t, const char *name, long long value)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.set_option(name ? name : "", value)); });
+}
 int rk_tree_digest(rk_tree *t, uint64_t out[8])
 {
     return guarded(t, [&]() { RK_WITH(t, T.digest(out)); });

@@ -178,14 +178,19 @@ struct build_arrays {
     dbuf<u32> crit_node;  // BFS index of each critical node
     dbuf<u32> crit_begin; // n_crit + 1 (crit_begin[n_crit] = n)
     dbuf<double> chunksum; // 4 doubles per chunk of PROPS_CHUNK particles
-    dbuf<double> nodesum;  // 4 doubles per node (experimental bottom-up node properties only)
+    dbuf<double> nodesum;  // 4 doubles per node (bottom-up node properties)
+    int props_bottom_up = -1; // node properties: -1 by size (bottom-up from PROPS_BOTTOMUP_MIN particles), 0 / 1 forced
     level_table levels;
     dbuf<dev_error> d_err;
     dbuf<u32> d_misc; // [0..1] abs-max bits (u64), [2] max group size
 };
 
 constexpr int PROPS_CHUNK = 256;
-constexpr int TOPO_TILE = 1024;
+constexpr size_t PROPS_BOTTOMUP_MIN = size_t(8) << 20;
+#ifndef RK_TOPO_TILE
+#define RK_TOPO_TILE 256
+#endif
+constexpr int TOPO_TILE = RK_TOPO_TILE; // particles per CTA of the node count / emit kernels
 
 // Kernels are wrapped in launch functions so that capi.cu stays free of <<<>>> syntax details.
 template <typename F>

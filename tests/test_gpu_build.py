@@ -208,3 +208,40 @@ def test_sample_sort_building_blocks_single_device(oracle_mod, rk):
     for j in range(3):
         assert (a[j] == b[j]).all()
     assert (g.crit_begin_at([0, g.ncrit_nodes]) == [0, N]).all()
+
+
+@pytest.mark.parametrize("fp,mac,n", [(32, "bh", 200000), (64, "bh_geom", 100000), (32, "bh_geom", 50000)])
+@pytest.mark.parametrize("bottom_up", [0, 1])
+def test_node_properties_both_reductions(oracle_mod, rk, fp, mac, n, bottom_up):
+    """Node properties top-down (small trees) and bottom-up (large trees, one launch per level): both within the
+    reference's own summation error of the oracle, and both with a mass-independent reduction tree (scaling every mass
+    by a power of two scales every node mass exactly, test/update_masses.cpp:56-68)."""
+    m, x, y, z = oracle_mod.plummer(n, fp=fp)
+    o = oracle_mod.OracleTree(x, y, z, m, fp=fp, mac=mac)
+    g = rk.Octree(fp=fp, mac=mac)
+    g.set_option("props_bottom_up", bottom_up)
+    g.build(x, y, z, m)
+    assert_same_tree(o, g, 4 * float(np.finfo(o.F).eps))
+    n1 = g.nodes()
+    g.update_masses((g.parts()[3] * 4).astype(o.F))
+    n2 = g.nodes()
+    assert (n2["props"][:, 3] == n1["props"][:, 3] * 4).all()
+    assert (n2["props"][:, :3] == n1["props"][:, :3]).all()
+
+
+def test_digest_and_crit_lower_bound(oracle_mod, rk):
+    m, x, y, z = oracle_mod.plummer(150000)
+    a, b = rk.Octree(), rk.Octree()
+    a.build(x, y, z, m)
+    b.build(x, y, z, m)
+    assert (a.digest() == b.digest()).all() and a.digest()[:7].all()
+    x2 = x.copy()
+    x2[777] += 1e-3
+    b.build(x2, y, z, m)
+    assert (a.digest() != b.digest()).any()
+    cb = a.crit()[:, 1].astype(np.int64)
+    q = np.array([0, 1, cb[5], cb[5] + 1, cb[-1], cb[-1] + 1, a.nparts], dtype=np.int64)
+    assert (a.crit_lower_bound(q).astype(np.int64) == np.searchsorted(cb, q, side="left")).all()
+    assert "traverse_kernel" not in a.last_kernel()
+    a.acc_pot(0, 0.75)
+    assert a.last_kernel().startswith("traverse_kernel<float,Q=0,MAC=0")
