@@ -5,7 +5,7 @@ NVFLAGS   = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidde
 CSRC      = rakau_b200/csrc
 OBJDIR    = build
 LIB       = rakau_b200/lib/librakau_b200.so
-OBJS      = $(OBJDIR)/sort.o $(OBJDIR)/build.o $(OBJDIR)/traverse.o $(OBJDIR)/capi.o $(OBJDIR)/plummer.o
+OBJS      = $(OBJDIR)/sort.o $(OBJDIR)/build.o $(OBJDIR)/traverse.o $(OBJDIR)/leapfrog.o $(OBJDIR)/capi.o $(OBJDIR)/plummer.o
 
 all: $(LIB) oracle
 

@@ -85,6 +85,13 @@ typedef struct rk_eval_info {
     float ms_total;        /* kernel + output scatter/copies issued by the call */
 } rk_eval_info;
 
+typedef struct rk_leapfrog_info {
+    float ms_step; /* CUDA-event time of the whole step */
+    float ms_integrals, ms_kick_drift, ms_rebuild, ms_traverse, ms_reindex;
+    uint64_t interactions, n_nodes;
+    double com[3], com_v[3], energy; /* track_integrals: values at the BEGINNING of the step (benchmark_leapfrog.cpp:292-347) */
+} rk_leapfrog_info;
+
 /* ---- the reference's seam ---------------------------------------------------------------------------- */
 /* cuda_device_count(), src/rakau_cuda.cu:32 — 0 on any CUDA error. */
 RK_API unsigned rk_device_count(void);
@@ -210,6 +217,19 @@ RK_API int rk_traverse_external_tree(int fp_bits, int mac, int Q, void *const ou
                                      const uint64_t *codes, size_t nparts, double mac_value, double G, double eps2,
                                      int offset_output, size_t ncrit, rk_eval_info *info, char *errbuf,
                                      size_t errbuf_len);
+
+/* ---- device-resident kick-drift-kick integrator: the time loop of benchmark/benchmark_leapfrog.cpp:252-384 ------- */
+/* Velocities (ORIGINAL particle order, host or device) are re-ordered into the tree's order (`reorder`, 252-267) and
+ * kept on the device; the initial accelerations (and potentials when track_integrals) are computed (282). The tree must
+ * have been built; theta / G / eps are used by every later evaluation. */
+RK_API int rk_tree_leapfrog_init(rk_tree *t, const void *vx, const void *vy, const void *vz, int where, double theta,
+                                 double G, double eps, int track_integrals);
+/* One step: [conserved quantities 292-347] kick 349-356, drift = update_particles_u functor 359-370 + sync 3678-3743
+ * (rebuild), accelerations 372, velocity update through last_perm 375-383. Nothing crosses PCIe. */
+RK_API int rk_tree_leapfrog_step(rk_tree *t, double dt, rk_leapfrog_info *info);
+/* what: 0 velocities, 1 accelerations of the last evaluation, 2 kicked velocities of the last step (in the order before
+ * that step's rebuild), 3 potentials in `a` (track_integrals); tree order; NULL pointers are skipped. */
+RK_API int rk_tree_leapfrog_get(rk_tree *t, int what, void *a, void *b, void *c, int where);
 
 /* ---- synthetic inputs of the reference's benchmarks (host only) ------------------------------------------ */
 /* Plummer sphere of benchmark/common.hpp:39-126. mode 0: sequential branch (first = 0, count = n_total);

@@ -36,6 +36,7 @@ SYMBOLS = [
     "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
     "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
     "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak", "rk_tree_set_option",
+    "rk_tree_leapfrog_init", "rk_tree_leapfrog_step", "rk_tree_leapfrog_get",
 ]
 
 
@@ -56,6 +57,18 @@ class EvalInfo(C.Structure):
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class LeapfrogInfo(C.Structure):
+    _fields_ = [("ms_step", C.c_float), ("ms_integrals", C.c_float), ("ms_kick_drift", C.c_float),
+                ("ms_rebuild", C.c_float), ("ms_traverse", C.c_float), ("ms_reindex", C.c_float),
+                ("interactions", C.c_uint64), ("n_nodes", C.c_uint64), ("com", C.c_double * 3),
+                ("com_v", C.c_double * 3), ("energy", C.c_double)]
+
+    def asdict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["com"], d["com_v"] = list(self.com), list(self.com_v)
+        return d
 
 
 class RakauError(Exception):
@@ -124,6 +137,9 @@ def lib():
     L.rk_tree_crit_lower_bound.argtypes = [vp, vp, sz, vp]
     L.rk_tree_digest.argtypes = [vp, vp]
     L.rk_tree_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    L.rk_tree_leapfrog_init.argtypes = [vp, vp, vp, vp, i32, dbl, dbl, dbl, i32]
+    L.rk_tree_leapfrog_step.argtypes = [vp, dbl, C.POINTER(LeapfrogInfo)]
+    L.rk_tree_leapfrog_get.argtypes = [vp, i32, vp, vp, vp, i32]
     L.rk_tree_last_kernel.restype = C.c_char_p
     L.rk_tree_last_kernel.argtypes = [vp]
     L.rk_measure_fp64_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
@@ -334,6 +350,24 @@ class Octree:
         self._check(rc)
         return out
 
+    # ---- device-resident leapfrog (benchmark_leapfrog.cpp:252-384) ----
+    def leapfrog_init(self, vx, vy, vz, theta, G=1.0, eps=0.0, track_integrals=False, where=RK_HOST):
+        arrs = [self._prep(a, where) for a in (vx, vy, vz)]
+        self._check(self.L.rk_tree_leapfrog_init(self.h, *[_ptr(a) for a in arrs], where, float(theta), float(G),
+                                                 float(eps), int(track_integrals)))
+
+    def leapfrog_step(self, dt):
+        info = LeapfrogInfo()
+        self._check(self.L.rk_tree_leapfrog_step(self.h, float(dt), C.byref(info)))
+        return info
+
+    def leapfrog_get(self, what):
+        """what: 0 velocities, 1 accelerations, 2 kicked velocities (order before the last rebuild), 3 potentials."""
+        out = [np.empty(self.nparts, dtype=self.F) for _ in range(1 if what == 3 else 3)]
+        ptrs = [_ptr(a) for a in out] + [None] * (3 - len(out))
+        self._check(self.L.rk_tree_leapfrog_get(self.h, what, *ptrs, RK_HOST))
+        return out
+
     def exact(self, idx, G=1.0, eps=0.0, ordered=False):
         out = np.zeros(4, dtype=np.float64)
         self._check(self.L.rk_tree_exact(self.h, idx, int(ordered), float(G), float(eps), _ptr(out)))
@@ -428,3 +462,53 @@ def plummer_leapfrog(n, a=1.0, fp=32):
     if rc:
         raise ValueError("rk_plummer_leapfrog: invalid arguments")
     return [o[:kept.value] for o in out]
+
+
+Leapfrog = True  # the device-resident integrator is part of this build (bench.py checks for it)
+
+
+def leapfrog_benchmark(n, steps, theta=0.75, max_leaf_n=16, ncrit=128, device=0, dt=1e-4, e2e_steps=3):
+    """BASELINE config 4: the reference's benchmark_leapfrog (Plummer sphere with velocities clipped at 10 core radii,
+    equal masses, eps = 0.45 N^-0.73, kick-drift-kick with a tree rebuild every step).
+    device_resident: rk_tree_leapfrog_step (nothing crosses PCIe). e2e_host_functors: the structure of the reference's
+    own loop - positions read back (p_its_u), kicked/drifted by host code, rk_tree_update_positions from host buffers,
+    accelerations written to host buffers, velocities updated on the host through last_perm."""
+    import statistics
+    import time
+    t0 = time.time()
+    x, y, z, vx, vy, vz = plummer_leapfrog(n)
+    gen_s = time.time() - t0
+    kept = x.size
+    m = np.full(kept, np.float32(1) / np.float32(kept), dtype=np.float32)
+    eps = float(np.float32(0.45) * np.float32(kept) ** np.float32(-0.73))
+    t = Octree(fp=32, mac="bh", device=device)
+    t.build(x, y, z, m, max_leaf_n=max_leaf_n, ncrit=ncrit)
+    t.leapfrog_init(vx, vy, vz, theta, eps=eps)
+    infos = [t.leapfrog_step(dt).asdict() for _ in range(steps + 2)][2:]
+    med = lambda k: float(statistics.median(i[k] for i in infos))  # noqa: E731
+    res = {"nparts_requested": n, "nparts": int(kept), "steps": steps, "dt": dt, "eps": eps, "generator_s": gen_s,
+           "device_resident": {"ms_per_step": med("ms_step"), "ms_kick_drift": med("ms_kick_drift"),
+                               "ms_rebuild": med("ms_rebuild"), "ms_traverse": med("ms_traverse"),
+                               "ms_reindex": med("ms_reindex"), "interactions_per_step": infos[-1]["interactions"],
+                               "kernel": t.last_kernel()}}
+    # ---- the reference's structure: host functors around update_particles_u ----
+    acc = [np.empty(kept, dtype=np.float32) for _ in range(3)]
+    v = [a.copy() for a in t.leapfrog_get(0)]
+    t.acc_pot(0, theta, eps=eps, out=acc)
+    half = np.float32(dt / 2)
+    ts = []
+    for s in range(e2e_steps + 1):
+        t0 = time.time()
+        kv = [a * half + b for a, b in zip(acc, v)]
+        pos = t.parts()
+        t.update_positions(*[k * np.float32(dt) + p for k, p in zip(kv, pos[:3])])
+        t.acc_pot(0, theta, eps=eps, out=acc)
+        lp = t.perm(RK_LAST_PERM).astype(np.int64)
+        v = [a * half + k[lp] for a, k in zip(acc, kv)]
+        ts.append(time.time() - t0)
+    res["e2e_host_functors"] = {"ms_per_step": 1e3 * float(statistics.median(ts[1:])), "steps": e2e_steps,
+                                "h2d_bytes_per_step": 12 * int(kept), "d2h_bytes_per_step": (16 + 12 + 8) * int(kept),
+                                "note": "host kick/drift/velocity update in numpy (single thread) between "
+                                        "rk_tree_get_parts, rk_tree_update_positions and rk_tree_acc_pot with host buffers"}
+    t.close()
+    return res

@@ -67,7 +67,7 @@ public:
         RK_CUDA_CHECK(cudaStreamCreateWithFlags(&m_own_stream, cudaStreamNonBlocking));
         m_stream = m_own_stream;
         m_ev.init();
-        RK_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m_hpin), 64 * sizeof(u64)));
+        RK_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m_hpin), 64 * sizeof(u64))); // [40..46]: leapfrog integrals
         m_b.d_err.reserve(2);
         m_b.d_misc.reserve(8);
         m_counters.reserve(40);
@@ -83,6 +83,11 @@ public:
         }
         if (m_sc.h_ghist) {
             cudaFreeHost(m_sc.h_ghist);
+        }
+        for (auto &e : m_lf_ev) {
+            if (e) {
+                cudaEventDestroy(e);
+            }
         }
         if (m_own_stream) {
             cudaStreamDestroy(m_own_stream);
@@ -129,6 +134,7 @@ public:
         m_costs_valid = false;
         m_cuts_valid = false;
         m_have_inv = false; // sort_shard / traverse_external write a new permutation
+        m_lf_ready = false;
         m_h_crit_begin.clear();
     }
 
@@ -979,6 +985,135 @@ public:
         std::memcpy(out4, m_hpin + 16, 4 * sizeof(double));
     }
 
+    // ---- device-resident leapfrog, benchmark_leapfrog.cpp:252-384 -------------------------------------------------
+    // init: velocities given in the ORIGINAL particle order are re-ordered with the tree's permutation (the `reorder`
+    // helper, 252-267) and the initial accelerations (+ potentials) are computed (282).
+    void leapfrog_init(const void *vx, const void *vy, const void *vz, int where, double theta, double G, double eps,
+                       bool track)
+    {
+        use();
+        const size_t n = m_b.n;
+        if (!n) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_leapfrog_init: the tree is empty");
+        }
+        for (int j = 0; j < 3; ++j) {
+            m_lf_v[j].reserve(n, 1.05);
+            m_lf_kv[j].reserve(n, 1.05);
+        }
+        for (int j = 0; j < 4; ++j) {
+            m_lf_acc[j].reserve(n, 1.05);
+        }
+        m_lf_scratch.reserve(lf_scratch_doubles());
+        if (!m_lf_ev[0]) {
+            for (auto &e : m_lf_ev) {
+                RK_CUDA_CHECK(cudaEventCreate(&e));
+            }
+        }
+        const F *dx, *dy, *dz, *dm;
+        upload4(vx, vy, vz, nullptr, n, where, dx, dy, dz, dm); // (staging buffers: free once the tree is built)
+        const F *in[3] = {dx, dy, dz};
+        F *out[3] = {m_lf_v[0].p, m_lf_v[1].p, m_lf_v[2].p};
+        launch_lf_reorder<F>(in, m_b.perm.p, out, n, m_stream);
+        m_lf_theta = theta;
+        m_lf_G = G;
+        m_lf_eps = eps;
+        m_lf_track = track;
+        m_lf_ready = true;
+        leapfrog_eval(nullptr);
+    }
+    void leapfrog_step(double dt_d, rk_leapfrog_info *info)
+    {
+        use();
+        if (!m_lf_ready || !m_b.n) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_leapfrog_step: call rk_tree_leapfrog_init first");
+        }
+        const size_t n = m_b.n;
+        const F dt = static_cast<F>(dt_d), half_dt = dt / F(2);
+        if (info) {
+            std::memset(info, 0, sizeof(*info));
+        }
+        const F *acc[3] = {m_lf_acc[0].p, m_lf_acc[1].p, m_lf_acc[2].p};
+        F *v[3] = {m_lf_v[0].p, m_lf_v[1].p, m_lf_v[2].p};
+        F *kv[3] = {m_lf_kv[0].p, m_lf_kv[1].p, m_lf_kv[2].p};
+        try {
+            RK_CUDA_CHECK(cudaEventRecord(m_lf_ev[0], m_stream));
+            // conserved quantities at the beginning of the step (292-347)
+            if (m_lf_track) {
+                launch_lf_integrals<F>(m_b.psorted.p, v, m_lf_acc[3].p, n, m_lf_scratch.p, m_stream);
+                RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 40, m_lf_scratch.p, 7 * sizeof(double), cudaMemcpyDeviceToHost,
+                                              m_stream));
+            }
+            RK_CUDA_CHECK(cudaEventRecord(m_lf_ev[1], m_stream));
+            // kick + drift (349-370), written into the pre-sort array of the rebuild; then sync() (3678-3743)
+            RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[0], m_stream));
+            reset_flags();
+            launch_lf_kick_drift<F>(acc, v, m_b.psorted.p, half_dt, dt, kv, m_b.pin.p, n,
+                                    reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
+            RK_CUDA_CHECK(cudaEventRecord(m_lf_ev[2], m_stream));
+            rk_build_info bi;
+            rebuild(false, &bi);
+            RK_CUDA_CHECK(cudaEventRecord(m_lf_ev[3], m_stream));
+            // accelerations in the new positions, then the second half kick through last_perm (372-383)
+            rk_eval_info ei;
+            leapfrog_eval(&ei);
+            RK_CUDA_CHECK(cudaEventRecord(m_lf_ev[4], m_stream));
+            launch_lf_kick_reindex<F>(acc, kv, m_b.last_perm, half_dt, v, n, m_stream);
+            RK_CUDA_CHECK(cudaEventRecord(m_lf_ev[5], m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+            if (info) {
+                cudaEventElapsedTime(&info->ms_step, m_lf_ev[0], m_lf_ev[5]);
+                cudaEventElapsedTime(&info->ms_integrals, m_lf_ev[0], m_lf_ev[1]);
+                cudaEventElapsedTime(&info->ms_kick_drift, m_lf_ev[1], m_lf_ev[2]);
+                cudaEventElapsedTime(&info->ms_rebuild, m_lf_ev[2], m_lf_ev[3]);
+                cudaEventElapsedTime(&info->ms_traverse, m_lf_ev[3], m_lf_ev[4]);
+                cudaEventElapsedTime(&info->ms_reindex, m_lf_ev[4], m_lf_ev[5]);
+                info->interactions = ei.interactions;
+                info->n_nodes = bi.n_nodes;
+                if (m_lf_track) {
+                    const double *h = reinterpret_cast<const double *>(m_hpin + 40);
+                    for (int j = 0; j < 3; ++j) {
+                        info->com[j] = h[j] / double(n);
+                        info->com_v[j] = h[3 + j] / double(n);
+                    }
+                    info->energy = h[6];
+                }
+            }
+        } catch (...) {
+            m_lf_ready = false;
+            throw;
+        }
+    }
+    // what: 0 velocities, 1 accelerations of the last evaluation, 2 kicked velocities of the last step (previous order),
+    // 3 potentials (track_integrals only); all in the tree's internal order.
+    void leapfrog_get(int what, void *a, void *b, void *c, int where)
+    {
+        use();
+        if (!m_lf_ready) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_leapfrog_get: call rk_tree_leapfrog_init first");
+        }
+        const size_t n = m_b.n;
+        const F *src[3] = {nullptr, nullptr, nullptr};
+        if (what == 0 || what == 1 || what == 2) {
+            dbuf<F> *arr = what == 0 ? m_lf_v : (what == 1 ? m_lf_acc : m_lf_kv);
+            for (int j = 0; j < 3; ++j) {
+                src[j] = arr[j].p;
+            }
+        } else if (what == 3 && m_lf_track) {
+            src[0] = m_lf_acc[3].p;
+        } else {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_leapfrog_get: invalid selector");
+        }
+        void *dst[3] = {a, b, c};
+        for (int j = 0; j < 3; ++j) {
+            if (dst[j] && src[j]) {
+                RK_CUDA_CHECK(cudaMemcpyAsync(dst[j], src[j], n * sizeof(F),
+                                              where == RK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                              m_stream));
+            }
+        }
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    }
+
     const char *last_kernel() const { return m_kernel_name; }
     void set_option(const std::string &name, long long value)
     {
@@ -1027,6 +1162,11 @@ public:
     }
 
 private:
+    void leapfrog_eval(rk_eval_info *ei)
+    {
+        void *out[4] = {m_lf_acc[0].p, m_lf_acc[1].p, m_lf_acc[2].p, m_lf_acc[3].p};
+        acc_pot(m_lf_track ? 2 : 0, false, m_lf_theta, m_lf_G, m_lf_eps, nullptr, 0, false, 0, 0, out, RK_DEVICE, ei);
+    }
     void reserve_particles(size_t n)
     {
         m_b.pin.reserve(n, 1.05);
@@ -1322,6 +1462,12 @@ private:
     u64 *m_hpin = nullptr; // pinned scratch for small read-backs
     std::vector<u32> m_h_crit_begin;
     char m_kernel_name[96] = "";
+    // leapfrog state: velocities / kicked velocities / accelerations (+ potentials) in the tree's internal order
+    dbuf<F> m_lf_v[3], m_lf_kv[3], m_lf_acc[4];
+    dbuf<double> m_lf_scratch;
+    cudaEvent_t m_lf_ev[6] = {};
+    double m_lf_theta = 0.75, m_lf_G = 1, m_lf_eps = 0;
+    bool m_lf_track = false, m_lf_ready = false;
 };
 
 } // namespace rk
@@ -1589,6 +1735,19 @@ const void *rk_tree_group_costs_device(rk_tree *t)
     return t->fp == 32 ? t->t32->group_costs_device() : t->t64->group_costs_device();
 }
 
+int rk_tree_leapfrog_init(rk_tree *t, const void *vx, const void *vy, const void *vz, int where, double theta, double G,
+                          double eps, int track_integrals)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.leapfrog_init(vx, vy, vz, where, theta, G, eps, track_integrals != 0)); });
+}
+int rk_tree_leapfrog_step(rk_tree *t, double dt, rk_leapfrog_info *info)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.leapfrog_step(dt, info)); });
+}
+int rk_tree_leapfrog_get(rk_tree *t, int what, void *a, void *b, void *c, int where)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.leapfrog_get(what, a, b, c, where)); });
+}
 int rk_tree_set_option(rk_tree *t, const char *name, long long value)
 {
     return guarded(t, [&]() { RK_WITH(t, T.set_option(name ? name : "", value)); });

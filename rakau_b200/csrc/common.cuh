@@ -238,6 +238,22 @@ void import_external_tree(build_arrays<F> &b, const void *d_nodes_aos, size_t tr
                           cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------
+// Leapfrog (leapfrog.cu): kick / drift / re-index / conserved quantities of benchmark_leapfrog.cpp:286-384
+// ---------------------------------------------------------------------------------------------------
+template <typename F>
+void launch_lf_reorder(const F *const in[3], const u32 *perm, F *const out[3], size_t n, cudaStream_t st);
+template <typename F>
+void launch_lf_kick_drift(const F *const acc[3], const F *const v[3], const vec4<F> *pos, F half_dt, F dt, F *const kv[3],
+                          vec4<F> *pin, size_t n, u64 *absmax, cudaStream_t st);
+template <typename F>
+void launch_lf_kick_reindex(const F *const acc[3], const F *const kv[3], const u32 *last_perm, F half_dt, F *const v[3],
+                            size_t n, cudaStream_t st);
+// scratch[0..6] = sum x, y, z, vx, vy, vz, (m v^2 / 2 + pot); scratch needs lf_scratch_doubles() doubles.
+template <typename F>
+void launch_lf_integrals(const vec4<F> *pos, const F *const v[3], const F *pot, size_t n, double *scratch, cudaStream_t st);
+unsigned lf_scratch_doubles();
+
+// ---------------------------------------------------------------------------------------------------
 // Traversal (traverse.cu)
 // ---------------------------------------------------------------------------------------------------
 template <typename F>

@@ -1,0 +1,80 @@
+"""Device-resident leapfrog (rk_tree_leapfrog_*) against the oracle's update_positions path.
+
+The time loop of the reference's benchmark/benchmark_leapfrog.cpp:286-384 is restated here in numpy (fma emulated in
+extended precision) and drives the ORACLE tree with the accelerations the GPU computed, step by step: after every step
+the GPU tree (rebuilt on the device from the drifted particles) and the oracle tree (update_particles_u path,
+tree.hpp:3678-3765) must agree bit for bit in codes, both permutations and particle order, and the velocities the device
+kept must equal the reference formula. Accelerations are checked against the oracle's own evaluation within the
+north_star tolerance, the conserved quantities against numpy."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def fma32(a, b, c):
+    """fp32 fused multiply-add: the product of two floats is exact in extended precision."""
+    return (a.astype(np.longdouble) * np.longdouble(b) + c.astype(np.longdouble)).astype(np.float32)
+
+
+@pytest.mark.parametrize("track", [False, True])
+def test_ten_steps_match_the_oracle_update_path(oracle_mod, rk, track):
+    n0, dt, theta = 30000, np.float32(1e-3), 0.75
+    x, y, z, vx, vy, vz = rk.plummer_leapfrog(n0)
+    n = x.size
+    m = np.full(n, np.float32(1) / np.float32(n), dtype=np.float32)
+    eps = float(np.float32(0.45) * np.float32(n) ** np.float32(-0.73))  # benchmark_leapfrog.cpp:222
+    g = rk.Octree()
+    g.build(x, y, z, m)
+    o = oracle_mod.OracleTree(x, y, z, m)
+    assert (g.perm(0) == o.perm(0)).all()
+    g.leapfrog_init(vx, vy, vz, theta, eps=eps, track_integrals=track)
+    p0 = o.perm(0).astype(np.int64)
+    v = [a[p0] for a in (vx, vy, vz)]  # `reorder`, 252-267
+    for got, want in zip(g.leapfrog_get(0), v):
+        assert (got == want).all()
+    half = np.float32(dt / np.float32(2))
+    energies = []
+    for step in range(10):
+        acc = g.leapfrog_get(1)
+        pos = o.parts()
+        for a, b in zip(g.parts(), pos):
+            assert (a == b).all()
+        # T3-style check of the device accelerations on the oracle's tree of the same particles
+        oacc, _ = o.acc_pot(2 if track else 0, theta, eps=eps, nthreads=8)
+        rel = np.linalg.norm(np.stack(acc, 1).astype(np.float64) - np.stack(oacc[:3], 1), axis=1) / np.linalg.norm(
+            np.stack(oacc[:3], 1).astype(np.float64), axis=1)
+        assert np.median(rel) <= 1e-6 and np.quantile(rel, 0.999) <= 1e-4, (step, np.median(rel), rel.max())
+        if track:
+            pots = g.leapfrog_get(3)[0]
+            e_np = float(np.sum(0.5 * m[0] * (v[0].astype(np.float64) ** 2 + v[1].astype(np.float64) ** 2
+                                              + v[2].astype(np.float64) ** 2) + pots.astype(np.float64)))
+        kv = [fma32(a, half, b) for a, b in zip(acc, v)]
+        newpos = [fma32(k, dt, p) for k, p in zip(kv, pos[:3])]
+        info = g.leapfrog_step(float(dt))
+        o.update_positions(*newpos)
+        assert (g.codes() == o.codes()).all(), step
+        assert (g.perm(0) == o.perm(0)).all() and (g.perm(1) == o.perm(1)).all(), step
+        lp = o.perm(1).astype(np.int64)
+        acc_new = g.leapfrog_get(1)
+        v = [fma32(a, half, k[lp]) for a, k in zip(acc_new, kv)]
+        for got, want in zip(g.leapfrog_get(0), v):
+            assert (got == want).all(), step
+        for got, want in zip(g.leapfrog_get(2), kv):
+            assert (got == want).all(), step
+        assert info.ms_step > 0 and info.interactions > 0
+        if track:
+            assert abs(info.energy - e_np) <= 1e-5 * abs(e_np), (info.energy, e_np)
+            com = [float(np.mean(p.astype(np.float64))) for p in pos[:3]]
+            assert np.allclose(list(info.com), com, rtol=0, atol=1e-6)
+            energies.append(info.energy)
+    if track:
+        assert abs(energies[-1] - energies[0]) <= 1e-4 * abs(energies[0])  # the integrator conserves energy
+
+
+def test_leapfrog_needs_init(rk):
+    m, x, y, z = rk.plummer(2000)
+    g = rk.Octree()
+    g.build(x, y, z, m)
+    with pytest.raises(rk.RakauError):
+        g.leapfrog_step(1e-3)

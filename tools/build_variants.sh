@@ -12,7 +12,7 @@ for spec in "$@"; do
         $NV $flags -c rakau_b200/csrc/$f.cu -o build/variants/${f}_$name.o -Xptxas -v 2> build/variants/${f}_$name.log
       else cp build/$f.o build/variants/${f}_$name.o; fi
     done
-    $NV -shared -o rakau_b200/lib/variants/librakau_b200_$name.so build/variants/sort_$name.o build/variants/build_$name.o build/variants/traverse_$name.o build/capi.o build/plummer.o -lcudart_static -lpthread -ldl -lrt
+    $NV -shared -o rakau_b200/lib/variants/librakau_b200_$name.so build/variants/sort_$name.o build/variants/build_$name.o build/variants/traverse_$name.o build/leapfrog.o build/capi.o build/plummer.o -lcudart_static -lpthread -ldl -lrt
     echo "$name: $(grep -A1 'traverse_kernelIfLi0ELi0' build/variants/traverse_$name.log | grep -o 'Used [0-9]* registers' | head -1) $(grep -A2 'traverse_kernelIfLi0ELi0' build/variants/traverse_$name.log | grep -o '[0-9]* bytes spill stores' | head -1)" ) &
 done
 wait
