@@ -36,6 +36,7 @@
 #include "../rakau_b200.h"
 #include "detail/aligned_allocator.hpp"
 #include "detail/kwargs.hpp"
+#include "detail/simple_timer.hpp"
 
 namespace rakau
 {
@@ -490,6 +491,7 @@ private:
     void construct_impl(F box_size, bool box_size_deduced, const std::array<It, NDim + 1u> &its, size_type N,
                         size_type max_leaf_n, size_type ncrit)
     {
+        simple_timer st("overall tree construction");
         m_box_size = box_size;
         m_box_size_deduced = box_size_deduced;
         m_max_leaf_n = max_leaf_n;
@@ -510,6 +512,16 @@ private:
             throw_status(rc, msg);
         }
         m_box_size = static_cast<F>(info.box_size);
+        report_build(info);
+    }
+    // Device-side phases of one build (CUDA-event times), under the reference's phase names.
+    static void report_build(const rk_build_info &info)
+    {
+        simple_timer::report_ms("morton encoding", info.ms_encode);
+        simple_timer::report_ms("indirect code sorting", info.ms_sort);
+        simple_timer::report_ms("permute", info.ms_permute);
+        simple_timer::report_ms("node building", info.ms_topology + info.ms_props);
+        (void)info;
     }
 
     template <typename... KwArgs>
@@ -725,6 +737,7 @@ private:
     void acc_pot_dispatch(const std::array<It, nvecs_res<Q>> &out, F theta, F G, F eps,
                           const std::vector<double> &split) const
     {
+        simple_timer st("vector accs/pots computation");
         if (!m_h) {
             const_cast<tree *>(this)->ensure_handle(); // an empty tree still validates its arguments
         }
@@ -837,6 +850,7 @@ private:
         if (!m_h) {
             throw std::invalid_argument("exact_*: the tree is empty");
         }
+        simple_timer st("exact acc/pot computation");
         double out[4];
         check(rk_tree_exact(m_h, idx, Ordered ? 1 : 0, G, eps, out));
         return {static_cast<F>(out[0]), static_cast<F>(out[1]), static_cast<F>(out[2]), static_cast<F>(out[3])};
@@ -934,6 +948,7 @@ private:
     template <bool Ordered, typename Func>
     void update_particles_dispatch(Func &&f)
     {
+        simple_timer st("overall update_particles");
         try {
             fetch_parts();
             if constexpr (Ordered) {
@@ -951,6 +966,7 @@ private:
                 check(rk_tree_update_positions(m_h, m_parts[0].data(), m_parts[1].data(), m_parts[2].data(),
                                                m_parts[3].data(), RK_HOST, &info));
                 m_box_size = static_cast<F>(info.box_size);
+                report_build(info);
             }
             invalidate_mirrors();
         } catch (...) {
@@ -962,6 +978,7 @@ private:
     template <bool Ordered, typename Func>
     void update_masses_dispatch(Func &&f)
     {
+        simple_timer st("overall update_masses");
         try {
             fetch_parts();
             if constexpr (Ordered) {
@@ -1000,6 +1017,44 @@ public:
     void update_masses_o(Func &&f)
     {
         update_masses_dispatch<true>(std::forward<Func>(f));
+    }
+
+    // ---- extension (no counterpart in the reference's class): the time loop of the reference's
+    // benchmark/benchmark_leapfrog.cpp:252-384 with positions and velocities resident on the GPU -------------------
+    // Velocities in the ORIGINAL particle order; theta / G / eps apply to every later step.
+    template <typename... KwArgs>
+    void leapfrog_init(const F *vx, const F *vy, const F *vz, F mac_value, bool track_integrals, KwArgs &&... args)
+    {
+        const auto [G, eps, split] = parse_accpot_kwargs(std::forward<KwArgs>(args)...);
+        (void)split;
+        if (!m_h) {
+            throw std::invalid_argument("leapfrog_init: the tree is empty");
+        }
+        check(rk_tree_leapfrog_init(m_h, vx, vy, vz, RK_HOST, mac_value, G, eps, track_integrals ? 1 : 0));
+    }
+    // One kick-drift-kick step (tree rebuild included); returns the phase times and, with track_integrals, the centre
+    // of mass, its velocity and the total energy at the beginning of the step.
+    rk_leapfrog_info leapfrog_step(F timestep)
+    {
+        rk_leapfrog_info info;
+        const int rc = rk_tree_leapfrog_step(m_h, timestep, &info);
+        invalidate_mirrors();
+        if (rc != RK_OK) {
+            const std::string msg = rk_last_error(m_h);
+            clear();
+            throw_status(rc, msg);
+        }
+        return info;
+    }
+    // Velocities in the tree's internal (Morton) order, like p_its_u().
+    std::array<std::vector<F>, NDim> leapfrog_velocities_u() const
+    {
+        std::array<std::vector<F>, NDim> v;
+        for (auto &a : v) {
+            a.resize(nparts());
+        }
+        check(rk_tree_leapfrog_get(m_h, 0, v[0].data(), v[1].data(), v[2].data(), RK_HOST));
+        return v;
     }
 
     // Getters (tree.hpp:3818-3837).
