@@ -1051,6 +1051,17 @@ void window_levels(i8 *a, i8 *bbuf, i8 *lvl, size_t n, size_t w, cudaStream_t st
     window_final_kernel<<<g, 256, 0, st>>>(in, lvl, n, w + 1 - k); count_launch();
 }
 
+// out[perm[i]] = in[i]: results from Morton order to the original particle order (tree.hpp:3320-3330).
+template <typename F>
+__global__ void __launch_bounds__(256)
+    scatter_perm_kernel(const F *__restrict__ in, const u32 *__restrict__ perm, F *__restrict__ out, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        out[perm[i]] = in[i];
+    }
+}
+
 __device__ __forceinline__ u64 mix64(u64 x)
 {
     x ^= x >> 33;
@@ -1098,6 +1109,15 @@ __global__ void lower_bound_kernel(const u32 *__restrict__ arr, size_t n, const 
 // ---------------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------
+template <typename F>
+void launch_scatter_perm(const F *in, const u32 *perm, F *out, size_t n, cudaStream_t st)
+{
+    if (n) {
+        scatter_perm_kernel<F><<<div_up(n, 256), 256, 0, st>>>(in, perm, out, n); count_launch();
+    }
+}
+template void launch_scatter_perm<float>(const float *, const u32 *, float *, size_t, cudaStream_t);
+template void launch_scatter_perm<double>(const double *, const u32 *, double *, size_t, cudaStream_t);
 void launch_digest(const void *a, size_t bytes, u64 *out, cudaStream_t st)
 {
     if (bytes >= 4) {

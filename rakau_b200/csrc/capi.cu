@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -134,6 +135,7 @@ public:
         m_costs_valid = false;
         m_cuts_valid = false;
         m_have_inv = false; // sort_shard / traverse_external write a new permutation
+        ++m_epoch;
         m_lf_ready = false;
         m_h_crit_begin.clear();
     }
@@ -386,6 +388,7 @@ public:
             RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
             check_props_error(m_hpin[1]);
             m_costs_valid = false;
+            ++m_epoch;
         } catch (...) {
             clear();
             throw;
@@ -606,6 +609,12 @@ public:
                 throw api_error(RK_ERR_INVALID_ARGUMENT, "Null output pointer");
             }
         }
+        // split = {cpu, gpu0, gpu1, ...} with two or more accelerator shares: one process drives several devices, as
+        // the reference does (tree.hpp:3147-3198, src/rakau_cuda.cu:492-527)
+        if (!ranged && nsplit >= 3 && std::count_if(split + 2, split + nsplit, [](double v) { return v > 0.; }) > 0) {
+            acc_pot_multi(Q, ordered, mac_value, G, eps2, split, nsplit, out, where, info);
+            return;
+        }
 
         trav_params<F> p{};
         p.parts = m_b.psorted.p;
@@ -772,6 +781,236 @@ public:
         }
     }
 
+
+    // ---- one process, several devices: the reference's `split` kwarg (tree.hpp:3147-3198) ---------------------------
+    // split[0] is the CPU share of the reference; there is no CPU path here, so it is evaluated by the first
+    // accelerator together with split[1]. Accelerator j >= 1 is device (this tree's device + j) mod device count: it
+    // holds a mirror of the traversal arrays (copied over NVLink when the tree has changed), evaluates its contiguous
+    // Morton range of critical nodes - the cuts are the reference's: cumulative weights projected onto the particle
+    // indices and snapped to the next critical node - and its results are copied back into this device's output
+    // arrays. Runs are cut-independent (traverse.cu), so the result equals the one-device result bit for bit.
+    void acc_pot_multi(int Q, bool ordered, F mac_value, F G, F eps2, const double *split, size_t nsplit,
+                       void *const out[4], int where, rk_eval_info *info)
+    {
+        const size_t n = m_b.n, C = m_b.n_crit, nacc = nsplit - 1;
+        const int nres = Q == 0 ? 3 : (Q == 1 ? 1 : 4);
+        int ndev = 0;
+        RK_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+        // particle cuts -> critical-node cuts
+        std::vector<double> share(nacc);
+        share[0] = split[0] + split[1];
+        for (size_t j = 1; j < nacc; ++j) {
+            share[j] = split[j + 1];
+        }
+        const double total = std::accumulate(share.begin(), share.end(), 0.);
+        std::vector<uint64_t> pidx(nacc - 1), ccut(nacc + 1);
+        double run = 0;
+        for (size_t j = 0; j + 1 < nacc; ++j) {
+            run += share[j];
+            pidx[j] = static_cast<uint64_t>(run / total * static_cast<double>(n));
+        }
+        ccut[0] = 0;
+        ccut[nacc] = C;
+        for (size_t j = 0; j + 1 < nacc; j += 16) {
+            const size_t k = std::min<size_t>(16, nacc - 1 - j);
+            crit_lower_bound(pidx.data() + j, k, ccut.data() + 1 + j);
+        }
+        for (size_t j = 1; j <= nacc; ++j) {
+            ccut[j] = std::max(ccut[j], ccut[j - 1]);
+        }
+        std::vector<size_t> cidx(ccut.begin(), ccut.end());
+        std::vector<uint64_t> pcut(nacc + 1);
+        for (size_t j = 0; j <= nacc; j += 64) {
+            crit_begin_at(cidx.data() + j, std::min<size_t>(64, nacc + 1 - j), pcut.data() + j);
+        }
+        use();
+        for (int k = 0; k < nres; ++k) {
+            m_out[k].reserve(n, 1.05); // the peers copy their ranges in, also when this device's own share is empty
+        }
+        // mirrors
+        if (m_mirror.size() < nacc - 1) {
+            m_mirror.resize(nacc - 1);
+        }
+        for (size_t j = 1; j < nacc; ++j) {
+            if (ccut[j + 1] == ccut[j]) {
+                continue;
+            }
+            auto &mp = m_mirror[j - 1];
+            const int dev = (m_device + static_cast<int>(j)) % ndev;
+            if (!mp || mp->m_device != dev) {
+                mp.reset(new tree<F>(m_mac, dev));
+            }
+            mp->mirror_from(*this);
+        }
+        use();
+        // launch every share (asynchronously), own share last so that the peers start first
+        std::vector<rk_eval_info> infos(nacc);
+        for (size_t j = nacc; j-- > 0;) {
+            if (ccut[j + 1] == ccut[j]) {
+                continue;
+            }
+            tree<F> &T = j ? *m_mirror[j - 1] : *this;
+            T.launch_range(Q, mac_value, G, eps2, ccut[j], ccut[j + 1]);
+        }
+        // collect: peers copy their Morton range of the results into this device's arrays
+        for (size_t j = 1; j < nacc; ++j) {
+            if (ccut[j + 1] == ccut[j]) {
+                continue;
+            }
+            tree<F> &T = *m_mirror[j - 1];
+            T.use();
+            const size_t b = pcut[j], e = pcut[j + 1];
+            for (int k = 0; k < nres; ++k) {
+                RK_CUDA_CHECK(cudaMemcpyPeerAsync(m_out[k].p + b, m_device, T.m_out[k].p + b, T.m_device,
+                                                  (e - b) * sizeof(F), T.m_stream));
+            }
+            T.finish_range(&infos[j]);
+        }
+        use();
+        if (ccut[1] != ccut[0]) {
+            finish_range(&infos[0]);
+        }
+        // outputs: Morton order as computed, or scattered to the original order (tree.hpp:3320-3330)
+        for (int k = 0; k < nres; ++k) {
+            F *src = m_out[k].p;
+            if (ordered) {
+                m_out_ord[k].reserve(n, 1.05);
+                launch_scatter_perm<F>(m_out[k].p, m_b.perm.p, m_out_ord[k].p, n, m_stream);
+                src = m_out_ord[k].p;
+            }
+            RK_CUDA_CHECK(cudaMemcpyAsync(out[k], src, n * sizeof(F),
+                                          where == RK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, m_stream));
+        }
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        if (info) {
+            for (const auto &ei : infos) {
+                info->mac_tests += ei.mac_tests;
+                info->accepted += ei.accepted;
+                info->p2p_pairs += ei.p2p_pairs;
+                info->self_pairs += ei.self_pairs;
+                info->interactions += ei.interactions;
+                info->n_groups += ei.n_groups;
+                info->kernel_launches += ei.kernel_launches;
+                info->ms_kernel = std::max(info->ms_kernel, ei.ms_kernel);
+            }
+            info->ms_total = info->ms_kernel;
+        }
+    }
+    // Copy the traversal arrays of `src` (another device) into this tree when they have changed.
+    void mirror_from(const tree &src)
+    {
+        if (m_mirror_of == &src && m_mirror_epoch == src.m_epoch) {
+            return;
+        }
+        use();
+        const size_t n = src.m_b.n, M = src.m_b.n_nodes, C = src.m_b.n_crit;
+        m_b.n = n;
+        m_b.n_nodes = M;
+        m_b.n_crit = C;
+        m_box = src.m_box;
+        m_max_group = src.m_max_group;
+        m_ncrit = src.m_ncrit;
+        m_max_leaf_n = src.m_max_leaf_n;
+        m_b.psorted.reserve(n, 1.05);
+        m_b.nodeA.reserve(M, 1.1);
+        m_b.nodeB.reserve(M, 1.1);
+        m_b.crit_node.reserve(C, 1.1);
+        m_b.crit_begin.reserve(C + 1, 1.1);
+        RK_CUDA_CHECK(cudaStreamSynchronize(src.m_stream));
+        auto cp = [&](void *dst, const void *from, size_t bytes) {
+            if (bytes) {
+                RK_CUDA_CHECK(cudaMemcpyPeerAsync(dst, m_device, from, src.m_device, bytes, m_stream));
+            }
+        };
+        cp(m_b.psorted.p, src.m_b.psorted.p, n * sizeof(vec4<F>));
+        cp(m_b.nodeA.p, src.m_b.nodeA.p, M * sizeof(vec4<F>));
+        cp(m_b.nodeB.p, src.m_b.nodeB.p, M * sizeof(uint4));
+        if (m_mac == RK_MAC_BH_GEOM) {
+            m_b.node_delta.reserve(M, 1.1);
+            cp(m_b.node_delta.p, src.m_b.node_delta.p, M * sizeof(F));
+        }
+        cp(m_b.crit_node.p, src.m_b.crit_node.p, C * sizeof(u32));
+        cp(m_b.crit_begin.p, src.m_b.crit_begin.p, (C + 1) * sizeof(u32));
+        m_costs_valid = false;
+        m_mirror_of = &src;
+        m_mirror_epoch = src.m_epoch;
+    }
+    // Asynchronous evaluation of the critical nodes [c0, c1) into this tree's own result arrays (Morton order);
+    // finish_range() waits for it and returns the counters.
+    void launch_range(int Q, F mac_value, F G, F eps2, size_t c0, size_t c1)
+    {
+        use();
+        const size_t n = m_b.n, C = m_b.n_crit;
+        trav_params<F> p{};
+        p.parts = m_b.psorted.p;
+        p.nodeA = m_b.nodeA.p;
+        p.nodeB = m_b.nodeB.p;
+        p.node_delta = m_b.node_delta.p;
+        p.crit_node = m_b.crit_node.p;
+        p.crit_begin = m_b.crit_begin.p;
+        p.c0 = static_cast<u32>(c0);
+        p.c1 = static_cast<u32>(c1);
+        p.ncrit = static_cast<u32>(C);
+        p.work_counter = m_work.p;
+        for (int l = 0; l < NLEVELS; ++l) {
+            const F nd = m_box / static_cast<F>(u64(1) << l);
+            p.mac_tab[l] = (m_mac == RK_MAC_BH) ? (nd * nd) * mac_value : nd;
+        }
+        p.mac_value = mac_value;
+        p.eps2 = eps2;
+        p.G = G;
+        p.perm = nullptr;
+        if (!m_costs_valid) {
+            m_group_cost.reserve(C, 1.1);
+            RK_CUDA_CHECK(cudaMemsetAsync(m_group_cost.p, 0, C * sizeof(u64), m_stream));
+        }
+        p.group_cost = m_group_cost.p;
+        p.counters = reinterpret_cast<u64 *>(m_counters.p);
+        const u32 tmax = static_cast<u32>((std::min<size_t>(m_max_group, 256) + 31) / 32 * 32);
+        p.tmax = tmax ? tmax : 32;
+        p.err = m_work.p + 1;
+        p.window = trav_window(p.tmax, m_max_group);
+        if (p.window) {
+            m_steal.reserve(size_t(TRAV_STEAL_SLOTS) * 16 + 16 + size_t(TRAV_STEAL_SLOTS) * trav_stack_cap());
+            p.steal = m_steal.p;
+            p.steal_published = m_steal.p + size_t(TRAV_STEAL_SLOTS) * 16;
+            p.steal_front = p.steal_published + 16;
+            p.steal_k = TRAV_STEAL_SLOTS;
+            RK_CUDA_CHECK(cudaMemsetAsync(m_steal.p, 0, (size_t(TRAV_STEAL_SLOTS) * 16 + 16) * sizeof(u32), m_stream));
+        }
+        const int nres = Q == 0 ? 3 : (Q == 1 ? 1 : 4);
+        for (int j = 0; j < nres; ++j) {
+            m_out[j].reserve(n, 1.05);
+            p.out[j] = m_out[j].p;
+        }
+        RK_CUDA_CHECK(cudaMemsetAsync(m_work.p, 0, 8 * sizeof(u32), m_stream));
+        RK_CUDA_CHECK(cudaMemsetAsync(m_counters.p, 0, 8 * sizeof(u64), m_stream));
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[5], m_stream));
+        launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream, m_kernel_name);
+        RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
+        m_range_groups = c1 - c0;
+    }
+    void finish_range(rk_eval_info *info)
+    {
+        use();
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin + 8, m_work.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+        RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+        if (reinterpret_cast<const u32 *>(m_hpin + 8)[1]) {
+            throw api_error(RK_ERR_RUNTIME, "Traversal stack overflow in the CUDA kernel");
+        }
+        m_costs_valid = true;
+        std::memset(info, 0, sizeof(*info));
+        info->mac_tests = m_hpin[0];
+        info->accepted = m_hpin[1];
+        info->p2p_pairs = m_hpin[2];
+        info->self_pairs = m_hpin[3];
+        info->interactions = info->p2p_pairs + 2 * info->self_pairs + m_hpin[4];
+        info->n_groups = m_range_groups;
+        info->kernel_launches = 1;
+        RK_CUDA_CHECK(cudaEventElapsedTime(&info->ms_kernel, m_ev.ev[5], m_ev.ev[6]));
+        info->ms_total = info->ms_kernel;
+    }
 
     // ---- literal drop-in for cuda_acc_pot_impl (rakau_cuda.cu:348-528): traverse a host-built tree ----------
     // The DFS AoS node array of the reference is re-laid level-major on the host (O(M) loops), uploaded together
@@ -1351,6 +1590,7 @@ private:
         }
         m_cuts_valid = true;
         m_costs_valid = false;
+        ++m_epoch;
         m_have_inv = false;
         m_h_crit_begin.clear();
         if (info) {
@@ -1454,7 +1694,12 @@ private:
     F m_box = F(0);
     bool m_box_deduced = false;
     size_t m_max_leaf_n = 16, m_ncrit = 128, m_max_group = 0;
-    dbuf<F> m_out[4];
+    dbuf<F> m_out[4], m_out_ord[4];
+    // multi-device evaluation: mirrors of this tree on the other devices; on a mirror, what it mirrors
+    std::vector<std::unique_ptr<tree>> m_mirror;
+    const tree *m_mirror_of = nullptr;
+    unsigned long long m_epoch = 1, m_mirror_epoch = 0;
+    size_t m_range_groups = 0;
     dbuf<u64> m_group_cost, m_counters;
     dbuf<u32> m_work, m_steal;
     bool m_costs_valid = false, m_have_inv = false, m_pending_check_encode = false;

@@ -211,6 +211,8 @@ void launch_perm_first(const u32 *last_perm, u32 *perm, u32 *inv_perm, size_t n,
 void launch_perm_compose(const u32 *old_perm, const u32 *last_perm, u32 *new_perm, u32 *inv_perm, size_t n,
                          cudaStream_t st);
 void launch_iota(u32 *p, size_t n, cudaStream_t st);
+template <typename F>
+void launch_scatter_perm(const F *in, const u32 *perm, F *out, size_t n, cudaStream_t st);
 // out += sum over the 32-bit words w_i of the array of mix64(i, w_i): an order-independent fingerprint of a device array
 // (bytes must be a multiple of 4).
 void launch_digest(const void *a, size_t bytes, u64 *out, cudaStream_t st);

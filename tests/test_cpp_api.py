@@ -7,7 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CPP = os.path.join(ROOT, "tests", "cpp")
-BINS = ["readme_example", "test_basic", "test_update", "test_accuracy"]
+BINS = ["readme_example", "test_basic", "test_update", "test_accuracy", "test_split"]
 
 
 def build():

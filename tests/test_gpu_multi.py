@@ -39,3 +39,32 @@ def test_two_rank_cuts_survive_moving_particles():
     d = _two_ranks(["--perturb"])
     assert d["parity_checked"] is True, d.get("parity")
     assert d["tree"]["shard_cost_imbalance"] is not None and d["tree"]["shard_cost_imbalance"] < 1.2
+
+
+def test_split_across_devices_in_one_process(rk):
+    """The reference's `split` kwarg with one share per device (tree.hpp:3147-3198), one process driving them: equal to
+    the one-device evaluation bit for bit, ordered and unordered outputs, counters included."""
+    import numpy as np
+    ndev = rk.device_count()
+    if ndev < 2:
+        pytest.skip("needs two GPUs")
+    m, x, y, z = rk.plummer(400000)
+    g = rk.Octree()
+    g.build(x, y, z, m)
+    for ordered in (False, True):
+        want = g.acc_pot(2, 0.75, G=2.5, eps=0.01, ordered=ordered)
+        wi = g.eval_info.asdict()
+        for split in ([0.0] + [1.0] * ndev, [0.5, 2.0] + [1.0] * (ndev - 1)):
+            got = g.acc_pot(2, 0.75, G=2.5, eps=0.01, ordered=ordered, split=split)
+            gi = g.eval_info.asdict()
+            for a, b in zip(got, want):
+                assert (a == b).all(), (ordered, split)
+            for k in ("mac_tests", "accepted", "p2p_pairs", "self_pairs", "interactions", "n_groups"):
+                assert gi[k] == wi[k], (k, gi[k], wi[k])
+    # moved particles: the mirrors on the other devices follow the rebuild
+    px, py, pz, pm = g.parts()
+    g.update_positions(px + np.float32(1e-3), py, pz)
+    want = g.acc_pot(0, 0.75, ordered=True)
+    got = g.acc_pot(0, 0.75, ordered=True, split=[0.0] + [1.0] * ndev)
+    for a, b in zip(got, want):
+        assert (a == b).all()
