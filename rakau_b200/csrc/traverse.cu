@@ -78,6 +78,9 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #ifndef RK_STEAL
 #define RK_STEAL 1
 #endif
+#ifndef RK_BATCH_BIG
+#define RK_BATCH_BIG 64
+#endif
 #define RK_PRAGMA_(x) _Pragma(#x)
 #define RK_UNROLL_PRAGMA(n) RK_PRAGMA_(unroll n)
 // BATCH (template parameter of the kernel) = sources evaluated per consume step; the source ring holds 2 * BATCH
@@ -1188,17 +1191,17 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *na
 {
     // batches of 64 sources unless the larger ring costs a resident CTA (tmax = 256)
     size_t smem64 = 0, smem32 = 0;
-    const int occ64 = trav_occupancy<F, Q, MAC, 64>(p.tmax, smem64), occ32 = trav_occupancy<F, Q, MAC, 32>(p.tmax, smem32);
+    const int occ64 = trav_occupancy<F, Q, MAC, RK_BATCH_BIG>(p.tmax, smem64), occ32 = trav_occupancy<F, Q, MAC, 32>(p.tmax, smem32);
     const bool big = occ64 >= occ32 && occ64 > 0;
     int per_sm = big ? occ64 : occ32;
     if (name) {
         std::snprintf(name, 96, "traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> window=%u ctas_per_sm=%d",
-                      sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? 64 : 32, p.window, per_sm);
+                      sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? RK_BATCH_BIG : 32, p.window, per_sm);
     }
     static const bool debug = std::getenv("RK_DEBUG_LAUNCH") != nullptr;
     if (debug) {
         std::fprintf(stderr, "[rk] traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> CTAs/SM %d (64: %d with %zu B, 32: %d with %zu B) tmax %u window %u\n",
-                     sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? 64 : 32, per_sm, occ64, smem64, occ32, smem32, p.tmax,
+                     sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? RK_BATCH_BIG : 32, per_sm, occ64, smem64, occ32, smem32, p.tmax,
                      p.window);
     }
     if (per_sm < 1) {
@@ -1214,7 +1217,7 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *na
         return;
     }
     if (big) {
-        traverse_kernel<F, Q, MAC, 64><<<grid, TRAV_THREADS, smem64, st>>>(p);
+        traverse_kernel<F, Q, MAC, RK_BATCH_BIG><<<grid, TRAV_THREADS, smem64, st>>>(p);
     } else {
         traverse_kernel<F, Q, MAC, 32><<<grid, TRAV_THREADS, smem32, st>>>(p);
     }

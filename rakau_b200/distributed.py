@@ -48,6 +48,7 @@ class ShardedTree:
         self._push = None  # per-peer copy streams of the output exchange
         self._peer = None  # two sets of (capacity, buffers, per-buffer list of every rank's device pointer), or False
         self._peer_flip = 0
+        self._gpeer = None  # symmetric-memory full arrays of the build (codes, x, y, z, m, original index), or False
 
     # ---- build -------------------------------------------------------------------------------------------
     def build(self, x, y, z, m, first_index):
@@ -119,6 +120,19 @@ class ShardedTree:
         # The topology needs only the codes: gather them first, then gather the particle arrays on a side stream
         # while rk_tree_build_presorted builds the topology on this one (it waits for `ready` before the node
         # properties).
+        pushed = self._push_gather(n, n_b, offs, bc, (bx, by, bz, bm, bi)) if self.cuda and self.world > 1 else None
+        if pushed is not None:
+            fc, (fx, fy, fz, fm, fi), ready = pushed
+            self._ev.append(('all_gather_codes', self._rec()))
+            self.n = n
+            self.full_sorted = (fx, fy, fz, fm)
+            bi_ = self.tree.build_presorted(fx, fy, fz, fm, fc, fi, n, box, self.mln, self.ncrit,
+                                            parts_ready_event=ready.cuda_event)
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._ev.append(('topology_props_and_particle_gather', self._rec()))
+            self.cut_particles = None
+            self._build_id += 1
+            return bi_
         fc = gather('c', bc)
         self._ev.append(('all_gather_codes', self._rec()))
         ready = None
@@ -144,6 +158,73 @@ class ShardedTree:
         self.cut_particles = None
         self._build_id += 1
         return bi_
+
+    def _push_gather(self, n, n_b, offs, bc, parts):
+        """Gather of the sorted buckets with COPY-ENGINE pushes into peer memory instead of NCCL all-gathers: every
+        rank copies its bucket into the same slice of every peer's (symmetric-memory) full arrays, one stream per peer,
+        the codes first. An NCCL all-gather kernel competes with the topology kernels for the SMs (measured in round 1:
+        12.8 + 7.5 ms run one after the other, 18.4 ms overlapped); the copy engines do not. Two tiny barriers (NCCL, on
+        the side stream) tell the ranks that all codes / all particle arrays have arrived. Returns None when peer
+        memory is not available (then the collective path is used).
+        Reuse of the buffers across steps is safe: a rank starts pushing step k+1 only after the barrier that ends the
+        evaluation of step k, by which time every peer has finished reading the arrays of step k."""
+        torch, dist = self.torch, self.dist
+        if self._gpeer is False:
+            return None
+        keys = ('c', 'x', 'y', 'z', 'm', 'i')
+        dts = (torch.int64, self.dt, self.dt, self.dt, self.dt, torch.int32)
+        if self._gpeer is None or self._gpeer['cap'] < n:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                cap = int(n * 1.02) + 16
+                g = {'cap': cap}
+                for k, dtp in zip(keys, dts):
+                    t = symm_mem.empty(cap, dtype=dtp, device=self.dev)
+                    h = symm_mem.rendezvous(t, dist.group.WORLD)
+                    g[k] = (t, [int(p) for p in h.buffer_ptrs])
+                self._gpeer = g
+            except Exception as exc:  # noqa: BLE001
+                self._gpeer = False
+                self._peer_error = repr(exc)
+                return None
+        from . import device_copy_async
+        g = self._gpeer
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        if self._push is None:
+            self._push = [torch.cuda.Stream(device=self.dev) for _ in range(self.world)]
+        side = self._side
+        for s in self._push:
+            s.wait_stream(main)
+        off = int(offs[self.rank])
+
+        def push(key, t):
+            buf, ptrs = g[key]
+            esz = t.element_size()
+            for d in range(self.world):  # d = 0: this rank's own copy; then staggered over the peers
+                r = (self.rank + d) % self.world
+                if n_b:
+                    device_copy_async(ptrs[r] + off * esz, t.data_ptr(), n_b * esz, self._push[r].cuda_stream)
+            return buf[:n]
+
+        fc = push('c', bc)
+        for s in self._push:
+            side.wait_stream(s)
+        with torch.cuda.stream(side):
+            dist.barrier()
+        codes_ready = torch.cuda.Event()
+        codes_ready.record(side)
+        full = tuple(push(k, t) for k, t in zip(keys[1:], parts))
+        for s in self._push:
+            side.wait_stream(s)
+        with torch.cuda.stream(side):
+            dist.barrier()
+        ready = torch.cuda.Event()
+        ready.record(side)
+        main.wait_event(codes_ready)
+        self._keep_alive = (bc, parts)  # the sources of the pushes must outlive them
+        return fc, full, ready
 
     def _rec(self):
         if not self.cuda:
