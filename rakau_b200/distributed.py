@@ -48,6 +48,8 @@ class ShardedTree:
         self._push = None  # per-peer copy streams of the output exchange
         self._peer = None  # two sets of (capacity, buffers, per-buffer list of every rank's device pointer), or False
         self._peer_flip = 0
+        self._bar = None
+        self._bpeer = None  # symmetric-memory bucket arrays of the exchange, or False
         self._gpeer = None  # symmetric-memory full arrays of the build (codes, x, y, z, m, original index), or False
 
     # ---- build -------------------------------------------------------------------------------------------
@@ -80,16 +82,20 @@ class ShardedTree:
         bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=self.dev), bounds,
                             torch.tensor([n_loc], dtype=torch.int64, device=self.dev)])
         send = (bounds[1:] - bounds[:-1])
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send)
-        send_l, recv_l = send.tolist(), recv.tolist()
-        n_b = int(sum(recv_l))
+        exchanged = self._push_a2a(send, bounds, (codes, sx, sy, sz, sm, gidx)) if self.cuda and self.world > 1 else None
+        if exchanged is not None:
+            n_b, (bc, bx, by, bz, bm, bi) = exchanged
+        else:
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv, send)
+            send_l, recv_l = send.tolist(), recv.tolist()
+            n_b = int(sum(recv_l))
 
-        def a2a(t):
-            out = torch.empty(n_b, dtype=t.dtype, device=self.dev)
-            dist.all_to_all_single(out, t, output_split_sizes=recv_l, input_split_sizes=send_l)
-            return out
-        bc, bx, by, bz, bm, bi = (a2a(t) for t in (codes, sx, sy, sz, sm, gidx))
+            def a2a(t):
+                out = torch.empty(n_b, dtype=t.dtype, device=self.dev)
+                dist.all_to_all_single(out, t, output_split_sizes=recv_l, input_split_sizes=send_l)
+                return out
+            bc, bx, by, bz, bm, bi = (a2a(t) for t in (codes, sx, sy, sz, sm, gidx))
         self._ev.append(('all_to_all', self._rec()))
         # 4. sort the bucket (runs arrive in rank order => stable order of the single-GPU path)
         self.bucket.sort_shard(bx, by, bz, bm, n_b, box, codes=bc)
@@ -159,6 +165,61 @@ class ShardedTree:
         self._build_id += 1
         return bi_
 
+    def _push_a2a(self, send, bounds, arrays):
+        """Bucket exchange with copy-engine pushes: rank s writes its slice for rank r straight into r's bucket arrays
+        (symmetric memory) at the offset of the runs of the ranks before s, so the runs arrive in rank order as the
+        stable order needs. One all-gather of the P x P count matrix, one stream-ordered barrier. Returns None when
+        peer memory is not available."""
+        torch, dist = self.torch, self.dist
+        if self._bpeer is False:
+            return None
+        counts = torch.empty(self.world * self.world, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(counts, send.contiguous())
+        M = np.asarray(counts.tolist(), dtype=np.int64).reshape(self.world, self.world)  # M[s][r]: s sends r
+        n_b_all = M.sum(axis=0)
+        need = int(n_b_all.max())
+        if self._bpeer is None or self._bpeer['cap'] < need:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                cap = int(need * 1.25) + 16  # the same value on every rank: the rendezvous is collective
+                b = {'cap': cap}
+                for k, t in zip('cxyzmi', arrays):
+                    buf = symm_mem.empty(cap, dtype=t.dtype, device=self.dev)
+                    h = symm_mem.rendezvous(buf, dist.group.WORLD)
+                    b[k] = (buf, [int(p) for p in h.buffer_ptrs])
+                self._bpeer = b
+            except Exception as exc:  # noqa: BLE001
+                self._bpeer = False
+                self._peer_error = repr(exc)
+                return None
+        from . import device_copy_async
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        if self._push is None:
+            self._push = [torch.cuda.Stream(device=self.dev) for _ in range(self.world)]
+        for s in self._push:
+            s.wait_stream(main)
+        bnd = [int(v) for v in bounds.tolist()]
+        off_at = np.cumsum(M, axis=0) - M  # off_at[s][r]: where the run of s starts in the bucket of r
+        out = []
+        for k, t in zip('cxyzmi', arrays):
+            buf, ptrs = self._bpeer[k]
+            esz = t.element_size()
+            for d in range(self.world):
+                r = (self.rank + d) % self.world
+                cnt = int(M[self.rank][r])
+                if cnt:
+                    device_copy_async(ptrs[r] + int(off_at[self.rank][r]) * esz, t.data_ptr() + bnd[r] * esz, cnt * esz,
+                                      self._push[r].cuda_stream)
+            out.append(buf[:int(n_b_all[self.rank])])
+        for s in self._push:
+            self._side.wait_stream(s)
+        self._stream_barrier(self._side)
+        main.wait_stream(self._side)
+        self._keep_alive_a2a = arrays
+        return int(n_b_all[self.rank]), tuple(out)
+
     def _push_gather(self, n, n_b, offs, bc, parts):
         """Gather of the sorted buckets with COPY-ENGINE pushes into peer memory instead of NCCL all-gathers: every
         rank copies its bucket into the same slice of every peer's (symmetric-memory) full arrays, one stream per peer,
@@ -211,20 +272,27 @@ class ShardedTree:
         fc = push('c', bc)
         for s in self._push:
             side.wait_stream(s)
-        with torch.cuda.stream(side):
-            dist.barrier()
+        self._stream_barrier(side)
         codes_ready = torch.cuda.Event()
         codes_ready.record(side)
         full = tuple(push(k, t) for k, t in zip(keys[1:], parts))
         for s in self._push:
             side.wait_stream(s)
-        with torch.cuda.stream(side):
-            dist.barrier()
+        self._stream_barrier(side)
         ready = torch.cuda.Event()
         ready.record(side)
         main.wait_event(codes_ready)
         self._keep_alive = (bc, parts)  # the sources of the pushes must outlive them
         return fc, full, ready
+
+    def _stream_barrier(self, stream):
+        """A barrier in STREAM order that does not block the host: a one-element all-reduce on `stream`. (dist.barrier()
+        synchronises the device, so the host could not enqueue the work that is meant to overlap the copies: measured
+        at 8 GPUs, the particle pushes then ran before the topology kernels instead of underneath them.)"""
+        if self._bar is None:
+            self._bar = self.torch.zeros(1, dtype=self.torch.float32, device=self.dev)
+        with self.torch.cuda.stream(stream):
+            self.dist.all_reduce(self._bar)
 
     def _rec(self):
         if not self.cuda:
@@ -402,8 +470,7 @@ class ShardedTree:
         # every rank's pushes are ordered before its part of the barrier, so after it all slices have arrived
         for s in self._push:
             side.wait_stream(s)
-        with torch.cuda.stream(side):
-            dist.barrier()
+        self._stream_barrier(side)
         main.wait_stream(side)
         return info, out
 

@@ -64,7 +64,7 @@ def children(i):
 
 rng = np.random.default_rng(3)
 sel = rng.choice(len(runs), NS, replace=False)
-for variant in ("box", "exact"):
+for variant in ("box", "gbox", "exact"):
     S = dict(base_visits=0, p1_visits=0, p2_visits=0, frontier=0, inter=0, inter_shared=0, groups=0, runs=0, fmax=0,
              shared_src=0, p2_src=0)
     for ri in sel:
@@ -104,6 +104,15 @@ for variant in ("box", "exact"):
                 far = np.maximum(np.abs(lo - c), np.abs(hi - c)); dmax2 = (far ** 2).sum()
                 rej_all = mac_lh >= dmax2 * (1 + 2.0 ** -20)
                 acc_all = False
+            elif variant == "gbox":
+                # per-group bounding boxes: accepted by every group's box / failing at every group's farthest corner
+                acc_all = rej_all = True
+                for k in range(len(gs)):
+                    glo, ghi = T[k].min(0), T[k].max(0)
+                    gap = np.maximum(0, np.maximum(glo - c, c - ghi))
+                    far = np.maximum(np.abs(glo - c), np.abs(ghi - c))
+                    acc_all &= mac_lh < (gap ** 2).sum() * (1 - 2.0 ** -20)
+                    rej_all &= mac_lh >= (far ** 2).sum() * (1 + 2.0 ** -20)
             else:
                 # a node that is a group's own node or its ancestor is neither accepted nor tested by that group
                 special = any(beg[i] <= beg[g] and end[g] <= end[i] for g in gs)
