@@ -177,6 +177,10 @@ constexpr size_t SCATTER_SMEM = size_t(SORT_TILE) * 12 + size_t(SORT_WARPS) * 25
 constexpr int OS_IPT = RK_SORT_IPT;
 constexpr int OS_TILE = SORT_THREADS * OS_IPT;
 constexpr int OS_SPAN = 32 * OS_IPT; // consecutive keys per warp
+#ifndef RK_SORT_LB
+#define RK_SORT_LB 8
+#endif
+constexpr int OS_LB = RK_SORT_LB; // predecessors inspected per look-back round trip
 constexpr u32 OS_AGG = 1u << 30, OS_PREFIX = 2u << 30, OS_VALUE = (1u << 30) - 1u;
 
 // All eight digit histograms in one pass over the keys. A digit that is equal over the whole warp (the top digits of
@@ -287,20 +291,34 @@ __global__ void __launch_bounds__(SORT_THREADS)
             *st = tot | OS_PREFIX;
         } else {
             *st = tot | OS_AGG;
+            // Look back OS_LB tiles per round trip: the status words of the nearest OS_LB predecessors are loaded
+            // together (independent L2 accesses), then consumed nearest first; only a word that is not published yet
+            // is polled. One dependent load per predecessor made the pass latency-bound (most of the ~300 resident
+            // tiles have only published their own count when a tile looks back).
             const volatile u32 *pv = st - 256;
-            for (;;) {
-                u32 v, polls = 0;
-                do {
-                    v = *pv;
-                    if (++polls == (1u << 26)) {
-                        __trap(); // a predecessor never published: fail loudly instead of hanging the device
-                    }
-                } while ((v & ~OS_VALUE) == 0u);
-                excl += v & OS_VALUE;
-                if (v & OS_PREFIX) {
-                    break;
+            u32 remaining = tile, polls = 0;
+            bool found = false;
+            while (!found) {
+                u32 v[OS_LB];
+#pragma unroll
+                for (int j = 0; j < OS_LB; ++j) {
+                    v[j] = static_cast<u32>(j) < remaining ? pv[-256 * j] : OS_PREFIX; // before tile 0: prefix 0
                 }
-                pv -= 256;
+#pragma unroll
+                for (int j = 0; j < OS_LB; ++j) {
+                    if (!found) {
+                        while ((v[j] & ~OS_VALUE) == 0u) {
+                            v[j] = pv[-256 * j];
+                            if (++polls == (1u << 26)) {
+                                __trap(); // a predecessor never published: fail loudly instead of hanging the device
+                            }
+                        }
+                        excl += v[j] & OS_VALUE;
+                        found = (v[j] & OS_PREFIX) != 0u;
+                    }
+                }
+                pv -= 256 * OS_LB;
+                remaining = remaining > u32(OS_LB) ? remaining - OS_LB : 0u;
             }
             *st = (excl + tot) | OS_PREFIX;
         }
