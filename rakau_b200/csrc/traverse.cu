@@ -33,7 +33,8 @@
 //  (4) Issue slots: fp32 interactions use the sm_100a packed instructions FFMA2/FADD2/FMUL2 (two targets per
 //      register pair, sources through the broadcast operand form), halving the FP32 instructions issued; slices
 //      are chosen so that the slot count per lane is even whenever that costs no padding.
-//  (5) Batches of 64 sources (was 32) amortise the accumulator round trip; 5 CTAs/SM (96 registers).
+//  (5) Batches of 64 sources (was 32) amortise the accumulator round trip; 5 CTAs/SM (96 registers). Round 2: 128
+//      sources at 4 CTAs/SM (128 registers), see launch_one().
 // Measured dead ends are recorded in DESIGN.md (next-step node prefetch, per-leaf copy loops, 6 CTAs/SM,
 // 8-target register tiles).
 
@@ -73,20 +74,21 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #define RK_SKIP_EVAL 0
 #endif
 #ifndef RK_CTAS
-#define RK_CTAS 5
+#define RK_CTAS 4
 #endif
 #ifndef RK_STEAL
 #define RK_STEAL 1
 #endif
 #ifndef RK_BATCH_BIG
-#define RK_BATCH_BIG 64
+#define RK_BATCH_BIG 128
 #endif
 #define RK_PRAGMA_(x) _Pragma(#x)
 #define RK_UNROLL_PRAGMA(n) RK_PRAGMA_(unroll n)
 // BATCH (template parameter of the kernel) = sources evaluated per consume step; the source ring holds 2 * BATCH
-// entries: the batch being filled + room for one step's appends / scratch. 64 amortises the per-batch accumulator
-// round trip through shared memory better than 32 (-6 % kernel time at ncrit = 128); 32 is kept for the large
-// tmax configurations where the bigger ring would cost a resident CTA (chosen in launch_one()).
+// entries: the batch being filled + room for one step's appends / scratch. Larger batches amortise the per-batch
+// accumulator round trip through shared memory and the tile prologues: 64 was 6 % faster than 32, 128 (at 4 CTAs/SM,
+// which also frees 128 registers per thread) another 2.6 %; 32 is kept for the large tmax configurations where the
+// bigger ring would cost a resident CTA (chosen in launch_one()).
 #ifndef RK_STACK
 #define RK_STACK 512
 #endif
@@ -1208,19 +1210,21 @@ int trav_occupancy(u32 tmax, size_t &smem)
 template <typename F, int Q, int MAC>
 void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *name)
 {
-    // batches of 64 sources unless the larger ring costs a resident CTA (tmax = 256)
+    // batches of BIG sources (fp32: 128 at 4 CTAs/SM and 128 registers - measured 2.6 % faster at ncrit 128 and 7 % at
+    // ncrit 256 than 64 at 5 CTAs/SM and 96 registers; fp64: 64) unless the larger ring costs a resident CTA
+    constexpr int BIG = sizeof(F) == 4 ? RK_BATCH_BIG : 64;
     size_t smem64 = 0, smem32 = 0;
-    const int occ64 = trav_occupancy<F, Q, MAC, RK_BATCH_BIG>(p.tmax, smem64), occ32 = trav_occupancy<F, Q, MAC, 32>(p.tmax, smem32);
+    const int occ64 = trav_occupancy<F, Q, MAC, BIG>(p.tmax, smem64), occ32 = trav_occupancy<F, Q, MAC, 32>(p.tmax, smem32);
     const bool big = occ64 >= occ32 && occ64 > 0;
     int per_sm = big ? occ64 : occ32;
     if (name) {
         std::snprintf(name, 96, "traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> window=%u ctas_per_sm=%d",
-                      sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? RK_BATCH_BIG : 32, p.window, per_sm);
+                      sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? BIG : 32, p.window, per_sm);
     }
     static const bool debug = std::getenv("RK_DEBUG_LAUNCH") != nullptr;
     if (debug) {
         std::fprintf(stderr, "[rk] traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> CTAs/SM %d (64: %d with %zu B, 32: %d with %zu B) tmax %u window %u\n",
-                     sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? RK_BATCH_BIG : 32, per_sm, occ64, smem64, occ32, smem32, p.tmax,
+                     sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? BIG : 32, per_sm, occ64, smem64, occ32, smem32, p.tmax,
                      p.window);
     }
     if (per_sm < 1) {
@@ -1236,7 +1240,7 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *na
         return;
     }
     if (big) {
-        traverse_kernel<F, Q, MAC, RK_BATCH_BIG><<<grid, TRAV_THREADS, smem64, st>>>(p);
+        traverse_kernel<F, Q, MAC, BIG><<<grid, TRAV_THREADS, smem64, st>>>(p);
     } else {
         traverse_kernel<F, Q, MAC, 32><<<grid, TRAV_THREADS, smem32, st>>>(p);
     }
