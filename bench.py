@@ -523,6 +523,18 @@ def run_ours(args):
     clk = clocks.stop()
     e2e_tot_ms, e2e_ms, _ = timed(args.steps, True)
     kernel_name = tree.last_kernel()
+    pageable_ms = None
+    if world == 1:
+        # the same end-to-end call from PAGEABLE host memory (what the C++ API's std::vector arguments are)
+        pin, pout = [np.array(a) for a in hnp], [np.empty(nparts, dtype=np.float32) for _ in range(3)]
+        ts = []
+        for _ in range(6):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tree.build(pin[0], pin[1], pin[2], pin[3], max_leaf_n=args.max_leaf_n, ncrit=args.ncrit, where=rk.RK_HOST)
+            tree.acc_pot(0, args.theta, out=pout, where=rk.RK_HOST)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        pageable_ms = median(ts[1:])
 
     # whole-job interactions per step = sum over ranks
     inter = torch.tensor([infos[-1][0]["interactions"]], dtype=torch.float64, device=dev)
@@ -567,6 +579,7 @@ def run_ours(args):
                            "peak_source": "measured" if peaks else "fallback"},
         "e2e": {"value": e2e_value, "unit": "Ginteractions/s", "ms_per_step": e2e_tot_ms / args.steps,
                 "h2d_bytes_per_step": 16 * count, "d2h_bytes_per_step": state["d2h"],
+                "pageable_host_buffers_ms_per_step": pageable_ms,
                 "note": "per rank: its input shard in, the output slice it owns out" if world > 1 else "rk_tree_build + rk_tree_acc_pot with pinned HOST buffers: all inputs in, all outputs out"},
         "gpu_launches": int(launches), "clocks": clk,
         "vs_published_ms": {"note": "reference README traversal-only times, other hardware", "v100_ms": 95,

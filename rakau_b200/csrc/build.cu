@@ -1223,7 +1223,7 @@ void topology_count(build_arrays<F> &b, size_t max_leaf_n, size_t ncrit, cudaStr
         }
     }
     topo_count_kernel<<<ntiles, TOPO_TILE, 0, st>>>(b.delta.p, b.lvl_leaf.p, b.lvl_crit.p, n, ntiles, b.tilecnt.p); count_launch();
-    row_scan_kernel<<<NLEVELS + 1, 256, 0, st>>>(b.tilecnt.p, ntiles, b.rowtot.p); count_launch();
+    row_scan_wide_kernel<<<NLEVELS + 1, 1024, 0, st>>>(b.tilecnt.p, ntiles, b.rowtot.p); count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
 }
 

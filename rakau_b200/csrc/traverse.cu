@@ -79,6 +79,9 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #ifndef RK_STEAL
 #define RK_STEAL 1
 #endif
+#ifndef RK_F64_CTAS
+#define RK_F64_CTAS 3
+#endif
 #ifndef RK_BATCH_BIG
 #define RK_BATCH_BIG 128
 #endif
@@ -116,25 +119,10 @@ __device__ __forceinline__ float fast_rsqrt(float x)
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// fp64: MUFU.RSQ of the value rounded to fp32 (relative error 2^-22) refined by two Newton steps in fp64
-// (error^2 each: 2^-44, then below 2^-53), 10 instructions instead of the ~20 of the library rsqrt() with its special
-// cases. Squared distances outside the fp32 range (pairs closer than 1e-19 or farther than 1e19) take the library path.
-#ifndef RK_FP64_FAST_RSQRT
-#define RK_FP64_FAST_RSQRT 1
-#endif
-__device__ __forceinline__ double fast_rsqrt(double x)
-{
-#if RK_FP64_FAST_RSQRT
-    if (x > 1e-37 && x < 1e37) {
-        double y = static_cast<double>(fast_rsqrt(static_cast<float>(x)));
-        const double h = -0.5 * x;
-        y = y * fma(h, y * y, 1.5);
-        y = y * fma(h, y * y, 1.5);
-        return y;
-    }
-#endif
-    return rsqrt(x);
-}
+// fp64: the library rsqrt() (MUFU.RSQ64H + refinement). Measured dead ends on B200 (4 M particles, theta = 0.5, 36.3 ms
+// with this): seeding two fp64 Newton steps from the fp32 MUFU.RSQ (two F2F conversions per pair: 64.5 ms) or from
+// rsqrt.approx.ftz.f64 (60.1 ms).
+__device__ __forceinline__ double fast_rsqrt(double x) { return rsqrt(x); }
 
 __device__ __forceinline__ u32 warp_incl_scan(u32 v, int lane)
 {
@@ -440,7 +428,7 @@ __device__ __forceinline__ u32 warp_lower_bound(const u32 *__restrict__ arr, u32
 // come from phase 1 (tests/studies/two_phase_walk_study.py).
 // (fp64: the double4 rings and accumulators let 3 CTAs fit in shared memory, so the kernel may use 168 registers)
 template <typename F, int Q, int MAC, int BATCH_>
-__global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? 3 : RK_CTAS) traverse_kernel(const trav_params<F> p)
+__global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : RK_CTAS) traverse_kernel(const trav_params<F> p)
 {
     constexpr u32 BATCH = BATCH_, LCAP = 2 * BATCH_;
     extern __shared__ __align__(32) unsigned char smem_raw[];

@@ -8,6 +8,8 @@ res = {}
 for name, fp, Q, theta, eps, G, mac in (("config1_fp32_accs", 32, 0, 0.75, 0.0, 1.0, "bh"), ("config2_fp32_accs_pots_eps_G", 32, 2, 0.75, 0.01, 2.5, "bh"),
                                         ("config3_fp64_accs_theta0.5", 64, 0, 0.5, 0.0, 1.0, "bh"), ("fp32_accs_bh_geom", 32, 0, 0.75, 0.0, 1.0, "bh_geom"),
                                         ("fp32_pots", 32, 1, 0.75, 0.0, 1.0, "bh")):
+    if len(sys.argv) > 1 and not any(a in name for a in sys.argv[1:]):
+        continue
     dt = np.float32 if fp == 32 else np.float64
     h = [np.empty(n, dtype=dt) for _ in range(4)]
     rk.plummer(n, 0, n, fp=fp, out=[h[3], h[0], h[1], h[2]])
@@ -22,7 +24,7 @@ for name, fp, Q, theta, eps, G, mac in (("config1_fp32_accs", 32, 0, 0.75, 0.0, 
         bs.append(bi.ms_total); ks.append(t.eval_info.ms_kernel)
     b, k = sorted(bs[2:])[2], sorted(ks[2:])[2]
     inter = t.eval_info.interactions
-    res[name] = {"ms_build": round(b, 3), "ms_traverse": round(k, 3), "ms_eval": round(b + k, 3), "interactions": inter,
+    res[name] = {"kernel": t.last_kernel(), "ms_build": round(b, 3), "ms_traverse": round(k, 3), "ms_eval": round(b + k, 3), "interactions": inter,
                  "Ginteractions_per_s_kernel": round(inter / k / 1e6, 1)}
     print(name, res[name], flush=True)
     del t, d, out
