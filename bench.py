@@ -127,15 +127,23 @@ class ClockSampler:
 # reference arm / cpu baseline (the ONLY users of oracle/ in this file; the product library is not imported here)
 # ----------------------------------------------------------------------------------------------------------
 def exact_interactions(args, nparts, chunk):
-    """Interactions of one evaluation of the reference's tree, when the committed fixture holds them (config 1:
-    tests/golden/baseline_sizes.json, counted by the oracle on the reference's own tree)."""
-    if chunk or nparts != 4_000_000 or args.theta != 0.75 or args.max_leaf_n != 16 or args.ncrit != 128:
-        return None
+    """Interactions of one evaluation, when a committed count exists. Config 1: tests/golden/baseline_sizes.json, counted
+    by the oracle on the reference's own tree. Config 5 (128 M, chunked generator): the count of the CUDA kernel on the
+    device-built tree (profiles/r02_bench_1gpu.json, configs.strong_scaling_base_128M) - the kernel's counts equal the
+    oracle's on the same tree (T1) and the device tree differs from the reference's only in the last ulps of the node
+    COMs (a relative 1e-7 of the count at 4 M); counting 229 G interactions with the scalar oracle would take the
+    reference arm minutes of host time."""
+    if args.theta != 0.75 or args.max_leaf_n != 16 or args.ncrit != 128:
+        return None, None
+    if chunk == (1 << 20) and nparts == 128_000_000:
+        return 229285644471.0, "counted by the CUDA kernel on the device-built tree (profiles/r02_bench_1gpu.json)"
+    if chunk or nparts != 4_000_000:
+        return None, None
     try:
         fix = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_sizes.json")))
-        return float(fix["config1_fp32_accs"]["counters"]["interactions"])
+        return float(fix["config1_fp32_accs"]["counters"]["interactions"]), "exact (tests/golden/baseline_sizes.json)"
     except Exception:
-        return None
+        return None, None
 
 
 def cpu_reference_run(args, nparts, steps, warmup, target_seconds, chunk=0):
@@ -149,8 +157,7 @@ def cpu_reference_run(args, nparts, steps, warmup, target_seconds, chunk=0):
     import oracle  # noqa: test infrastructure, allowed here only
     cores = os.cpu_count() or 1
     m, x, y, z = oracle.plummer(nparts, chunk=chunk, nthreads=cores)
-    i_total = exact_interactions(args, nparts, chunk)
-    i_note = "exact (tests/golden/baseline_sizes.json)"
+    i_total, i_note = exact_interactions(args, nparts, chunk)
     otree, t_obuild, t_probe, cstride = None, 0.0, 0.0, 1
     variant = oracle.best_ref_variant()
     if i_total is None or variant is None:
@@ -459,7 +466,15 @@ def run_ours(args):
             state["bi"] = sharded.build(src[0], src[1], src[2], src[3], first_index=first)
             ev[1].record()
             # (outputs: library-owned peer-memory buffers, complete on every rank when the call returns)
-            state["info"], outs = sharded.acc_pot(0, args.theta)
+            # (end to end: each finished launch's slice of this rank's range goes to the pinned host buffers while the
+            # next launch runs)
+            rng = None
+            if e2e:
+                sharded.ensure_cuts()
+                rng = int(sharded.cut_particles[rank + 1]) - int(sharded.cut_particles[rank])
+                if hout[0].numel() < rng:
+                    hout[:] = [torch.empty(int(rng * 1.1), dtype=torch.float32).pin_memory() for _ in range(3)]
+            state["info"], outs = sharded.acc_pot(0, args.theta, host_out=hout if rng is not None else None)
             ev[2].record()
             state["phase_events"] = ev
             state["outs"] = outs
@@ -467,12 +482,13 @@ def run_ours(args):
         if e2e:
             if world > 1 and hout[0].numel() < hi - lo:  # the cost-weighted range of this rank outgrew the buffers
                 hout[:] = [torch.empty(int((hi - lo) * 1.1), dtype=torch.float32).pin_memory() for _ in range(3)]
-            for j in range(3):
-                if world == 1:
+            if world == 1:
+                for j in range(3):
                     hout[j][lo:hi].copy_(out_dev[j][lo:hi], non_blocking=True)
-                else:
+            elif rng is None:
+                for j in range(3):
                     hout[j][:hi - lo].copy_(outs[j][lo:hi], non_blocking=True)  # each rank returns the slice it owns
-            stream.synchronize()
+            stream.synchronize()  # (the per-launch copies were ordered before the end of acc_pot)
         state["d2h"] = 12 * (hi - lo)
 
     def refresh_costs():

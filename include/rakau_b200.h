@@ -136,6 +136,14 @@ RK_API int rk_tree_update_masses(rk_tree *t, const void *m, int where);
  * the codes alone, so the caller can gather the particle arrays on another stream underneath it. */
 RK_API int rk_tree_sort_shard(rk_tree *t, const void *x, const void *y, const void *z, const void *m,
                               const uint64_t *codes, size_t n, double box_size);
+/* The same exchange without the local pre-sort: rk_tree_encode_shard packs and Morton-encodes the shard (codes in input
+ * order, readable with rk_tree_get_codes_device, from which the ranks sample their splitters); rk_tree_partition_shard
+ * then groups the particles by splitter bucket with ONE stable radix pass on the bucket id (bucket = number of
+ * splitters <= code; nsplit <= 255 device-resident ascending splitters) and returns the nsplit + 1 bucket sizes in
+ * counts (host). Afterwards codes / particles / last_perm of the shard are in bucket order. */
+RK_API int rk_tree_encode_shard(rk_tree *t, const void *x, const void *y, const void *z, const void *m, size_t n,
+                                double box_size);
+RK_API int rk_tree_partition_shard(rk_tree *t, const uint64_t *splitters, unsigned nsplit, uint64_t *counts);
 RK_API int rk_tree_get_codes_device(rk_tree *t, uint64_t *out);
 RK_API int rk_tree_build_presorted(rk_tree *t, const void *x, const void *y, const void *z, const void *m,
                                    const uint64_t *codes, const uint32_t *perm, size_t n, double box_size,

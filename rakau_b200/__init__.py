@@ -36,7 +36,8 @@ SYMBOLS = [
     "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
     "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
     "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak", "rk_tree_set_option",
-    "rk_tree_leapfrog_init", "rk_tree_leapfrog_step", "rk_tree_leapfrog_get",
+    "rk_tree_leapfrog_init", "rk_tree_leapfrog_step", "rk_tree_leapfrog_get", "rk_tree_encode_shard",
+    "rk_tree_partition_shard",
 ]
 
 
@@ -132,6 +133,8 @@ def lib():
     L.rk_tree_get_perm_device.argtypes = [vp, i32, vp]
     L.rk_tree_sort_shard.argtypes = [vp, vp, vp, vp, vp, vp, sz, dbl]
     L.rk_tree_get_codes_device.argtypes = [vp, vp]
+    L.rk_tree_encode_shard.argtypes = [vp, vp, vp, vp, vp, sz, dbl]
+    L.rk_tree_partition_shard.argtypes = [vp, vp, C.c_uint, vp]
     L.rk_tree_build_presorted.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, dbl, sz, sz, vp, C.POINTER(BuildInfo)]
     L.rk_tree_crit_begin_at.argtypes = [vp, vp, sz, vp]
     L.rk_tree_crit_lower_bound.argtypes = [vp, vp, sz, vp]
@@ -268,6 +271,17 @@ class Octree:
         """Sort a device-resident shard with the global box (multi-GPU sample sort building block)."""
         self._check(self.L.rk_tree_sort_shard(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(m), _ptr(codes), n,
                                               float(box_size)))
+
+    def encode_shard(self, x, y, z, m, n, box_size):
+        """Pack + Morton-encode a device-resident shard with the global box (codes in input order: codes_device)."""
+        self._check(self.L.rk_tree_encode_shard(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(m), n, float(box_size)))
+
+    def partition_shard(self, splitters):
+        """Group the encoded shard by splitter bucket (one stable radix pass); returns the bucket sizes."""
+        nsplit = splitters.numel() if hasattr(splitters, "numel") else len(splitters)
+        counts = np.zeros(nsplit + 1, dtype=np.uint64)
+        self._check(self.L.rk_tree_partition_shard(self.h, _ptr(splitters), nsplit, _ptr(counts)))
+        return counts
 
     def codes_device(self, out):
         self._check(self.L.rk_tree_get_codes_device(self.h, _ptr(out)))

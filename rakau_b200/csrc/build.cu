@@ -1051,6 +1051,40 @@ void window_levels(i8 *a, i8 *bbuf, i8 *lvl, size_t n, size_t w, cudaStream_t st
     window_final_kernel<<<g, 256, 0, st>>>(in, lvl, n, w + 1 - k); count_launch();
 }
 
+// Bucket of a sample sort: the number of splitters <= code (splitters ascending, at most 255 of them).
+__global__ void __launch_bounds__(256) bucket_ids_kernel(const u64 *__restrict__ codes, size_t n,
+                                                         const u64 *__restrict__ splitters, unsigned nsplit,
+                                                         u64 *__restrict__ ids)
+{
+    __shared__ u64 sp[256];
+    if (threadIdx.x < nsplit) {
+        sp[threadIdx.x] = splitters[threadIdx.x];
+    }
+    __syncthreads();
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        const u64 c = codes[i];
+        unsigned lo = 0, hi = nsplit; // first splitter > c
+        while (lo < hi) {
+            const unsigned mid = (lo + hi) / 2;
+            if (sp[mid] <= c) {
+                lo = mid + 1;
+            } else {
+                hi = mid;
+            }
+        }
+        ids[i] = lo;
+    }
+}
+__global__ void __launch_bounds__(256) gather_u64_kernel(const u64 *__restrict__ in, const u32 *__restrict__ idx,
+                                                         u64 *__restrict__ out, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        out[i] = in[idx[i]];
+    }
+}
+
 // out[perm[i]] = in[i]: results from Morton order to the original particle order (tree.hpp:3320-3330).
 template <typename F>
 __global__ void __launch_bounds__(256)
@@ -1109,6 +1143,18 @@ __global__ void lower_bound_kernel(const u32 *__restrict__ arr, size_t n, const 
 // ---------------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------
+void launch_bucket_ids(const u64 *codes, size_t n, const u64 *splitters, unsigned nsplit, u64 *ids, cudaStream_t st)
+{
+    if (n) {
+        bucket_ids_kernel<<<div_up(n, 256), 256, 0, st>>>(codes, n, splitters, nsplit, ids); count_launch();
+    }
+}
+void launch_gather_u64(const u64 *in, const u32 *idx, u64 *out, size_t n, cudaStream_t st)
+{
+    if (n) {
+        gather_u64_kernel<<<div_up(n, 256), 256, 0, st>>>(in, idx, out, n); count_launch();
+    }
+}
 template <typename F>
 void launch_scatter_perm(const F *in, const u32 *perm, F *out, size_t n, cudaStream_t st)
 {

@@ -68,7 +68,7 @@ public:
         RK_CUDA_CHECK(cudaStreamCreateWithFlags(&m_own_stream, cudaStreamNonBlocking));
         m_stream = m_own_stream;
         m_ev.init();
-        RK_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m_hpin), 64 * sizeof(u64))); // [40..46]: leapfrog integrals
+        RK_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m_hpin), 192 * sizeof(u64))); // [40..46]: leapfrog integrals, [48..175]: bucket counts
         m_b.d_err.reserve(2);
         m_b.d_misc.reserve(8);
         m_counters.reserve(40);
@@ -292,6 +292,78 @@ public:
             RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
             if (!codes_dev) {
                 check_encode_error(m_hpin[0], inv_box);
+            }
+        } catch (...) {
+            clear();
+            throw;
+        }
+    }
+    // Sample-sort without the local pre-sort: (1) encode_shard packs and Morton-encodes the shard (codes readable
+    // with get_codes_device, in input order); the ranks agree on the splitters from samples of those codes;
+    // (2) partition_shard moves the particles of each splitter bucket together with ONE stable radix pass on the
+    // bucket id (instead of the eight passes of a full sort): bucket r is then a contiguous slice whose particles keep
+    // their input order, so the receiving rank's stable sort of (runs in rank order) reproduces the single-GPU order.
+    void encode_shard(const void *x, const void *y, const void *z, const void *m, size_t n, double box_size)
+    {
+        use();
+        clear();
+        const F bs = static_cast<F>(box_size);
+        if (!std::isfinite(bs) || bs <= F(0)) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_encode_shard needs the global box size");
+        }
+        m_box = bs;
+        m_b.n = n;
+        if (!n) {
+            return;
+        }
+        try {
+            reserve_particles(n);
+            reset_flags();
+            launch_pack_absmax<F>(static_cast<const F *>(x), static_cast<const F *>(y), static_cast<const F *>(z),
+                                  static_cast<const F *>(m), m_b.pin.p, n, reinterpret_cast<u64 *>(m_b.d_misc.p), m_stream);
+            launch_encode<F>(m_b.pin.p, m_b.keys_a.p, n, F(1) / m_box, m_b.d_err.p, m_stream);
+            m_b.codes = m_b.keys_a.p;
+            RK_CUDA_CHECK(cudaMemcpyAsync(m_hpin, m_b.d_err.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+            check_encode_error(m_hpin[0], F(1) / m_box);
+        } catch (...) {
+            clear();
+            throw;
+        }
+    }
+    void partition_shard(const uint64_t *splitters_dev, unsigned nsplit, uint64_t *counts_out)
+    {
+        use();
+        const size_t n = m_b.n;
+        if (nsplit > 255u || !counts_out) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_partition_shard: at most 255 splitters");
+        }
+        for (unsigned r = 0; r <= nsplit; ++r) {
+            counts_out[r] = 0;
+        }
+        if (!n) {
+            return;
+        }
+        if (m_b.codes != m_b.keys_a.p) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_partition_shard: call rk_tree_encode_shard first");
+        }
+        try {
+            // bucket ids -> keys_b; one stable pass: ids (unused afterwards) -> perm_tmp-sized scratch, permutation -> idx_a
+            launch_bucket_ids(m_b.keys_a.p, n, reinterpret_cast<const u64 *>(splitters_dev), nsplit, m_b.keys_b.p, m_stream);
+            m_ids_sorted.reserve(n, 1.05);
+            const u32 *counts_dev = nullptr;
+            radix_partition_pass(m_b.keys_b.p, m_ids_sorted.p, m_b.idx_a.p, n, m_sc, m_stream, &counts_dev);
+            // codes and particles in bucket order
+            launch_gather_u64(m_b.keys_a.p, m_b.idx_a.p, m_b.keys_b.p, n, m_stream);
+            m_b.codes = m_b.keys_b.p;
+            m_b.last_perm = m_b.idx_a.p;
+            launch_gather<F>(m_b.pin.p, m_b.idx_a.p, m_b.psorted.p, n, m_stream);
+            launch_perm_first(m_b.idx_a.p, m_b.perm.p, nullptr, n, m_stream);
+            u32 *h = reinterpret_cast<u32 *>(m_hpin + 48);
+            RK_CUDA_CHECK(cudaMemcpyAsync(h, counts_dev, 256 * sizeof(u32), cudaMemcpyDeviceToHost, m_stream));
+            RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+            for (unsigned r = 0; r <= nsplit; ++r) {
+                counts_out[r] = h[r];
             }
         } catch (...) {
             clear();
@@ -1702,6 +1774,7 @@ private:
     size_t m_range_groups = 0;
     dbuf<u64> m_group_cost, m_counters;
     dbuf<u32> m_work, m_steal;
+    dbuf<u64> m_ids_sorted; // partition_shard scratch
     bool m_costs_valid = false, m_have_inv = false, m_pending_check_encode = false;
     F m_pending_inv_box = F(0);
     u64 *m_hpin = nullptr; // pinned scratch for small read-backs
@@ -1858,6 +1931,14 @@ int rk_tree_sort_shard(rk_tree *t, const void *x, const void *y, const void *z, 
                        size_t n, double box_size)
 {
     return guarded(t, [&]() { RK_WITH(t, T.sort_shard(x, y, z, m, codes, n, box_size)); });
+}
+int rk_tree_encode_shard(rk_tree *t, const void *x, const void *y, const void *z, const void *m, size_t n, double box_size)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.encode_shard(x, y, z, m, n, box_size)); });
+}
+int rk_tree_partition_shard(rk_tree *t, const uint64_t *splitters, unsigned nsplit, uint64_t *counts)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.partition_shard(splitters, nsplit, counts)); });
 }
 int rk_tree_get_codes_device(rk_tree *t, uint64_t *out)
 {

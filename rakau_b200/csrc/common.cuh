@@ -134,6 +134,9 @@ struct sort_scratch {
 int radix_sort_pairs(u64 *keys_a, u64 *keys_b, u32 *idx_a, u32 *idx_b, size_t n, sort_scratch &sc, cudaStream_t st,
                      u64 **keys_out, u32 **idx_out);
 
+void radix_partition_pass(const u64 *keys_in, u64 *keys_out, u32 *idx_out, size_t n, sort_scratch &sc, cudaStream_t st,
+                          const u32 **counts_dev);
+
 // ---------------------------------------------------------------------------------------------------
 // Build (build.cu)
 // ---------------------------------------------------------------------------------------------------
@@ -211,6 +214,9 @@ void launch_perm_first(const u32 *last_perm, u32 *perm, u32 *inv_perm, size_t n,
 void launch_perm_compose(const u32 *old_perm, const u32 *last_perm, u32 *new_perm, u32 *inv_perm, size_t n,
                          cudaStream_t st);
 void launch_iota(u32 *p, size_t n, cudaStream_t st);
+// ids[i] = number of splitters <= codes[i] (the bucket of a sample sort, < 256); out[i] = in[idx[i]] for 64-bit words
+void launch_bucket_ids(const u64 *codes, size_t n, const u64 *splitters, unsigned nsplit, u64 *ids, cudaStream_t st);
+void launch_gather_u64(const u64 *in, const u32 *idx, u64 *out, size_t n, cudaStream_t st);
 template <typename F>
 void launch_scatter_perm(const F *in, const u32 *perm, F *out, size_t n, cudaStream_t st);
 // out += sum over the 32-bit words w_i of the array of mix64(i, w_i): an order-independent fingerprint of a device array

@@ -373,6 +373,31 @@ void launch_iota(u32 *p, size_t n, cudaStream_t st)
     }
 }
 
+// Stable partition of the indices 0 .. n-1 by an 8-bit bucket id held in the low byte of keys_in: ONE one-sweep pass.
+// idx_out receives the permutation, keys_out the permuted ids; counts_dev (256 u32, device) the bucket sizes.
+void radix_partition_pass(const u64 *keys_in, u64 *keys_out, u32 *idx_out, size_t n, sort_scratch &sc, cudaStream_t st,
+                          const u32 **counts_dev)
+{
+    const u32 nt = div_up(n, OS_TILE);
+    sc.ghist.reserve(8 * 256 + 8);
+    sc.tilehist.reserve(size_t(8) * 256 * (nt ? nt : 1), 1.25);
+    RK_CUDA_CHECK(cudaMemsetAsync(sc.ghist.p, 0, (8 * 256 + 8) * sizeof(u32), st));
+    *counts_dev = sc.ghist.p;
+    if (!n || n >= (size_t(1) << 30)) {
+        if (n) {
+            throw cuda_error(3, "radix_partition_pass: too many elements");
+        }
+        return;
+    }
+    RK_CUDA_CHECK(cudaMemsetAsync(sc.tilehist.p, 0, size_t(256) * nt * sizeof(u32), st));
+    hist8_kernel<<<148 * 2, 512, 0, st>>>(keys_in, n, sc.ghist.p); count_launch();
+    RK_CUDA_CHECK(cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(ONESWEEP_SMEM)));
+    onesweep_kernel<<<nt, SORT_THREADS, ONESWEEP_SMEM, st>>>(keys_in, nullptr, keys_out, idx_out, n, 0, sc.ghist.p,
+                                                            sc.tilehist.p, sc.ghist.p + 8 * 256); count_launch();
+    RK_CUDA_CHECK(cudaGetLastError());
+}
+
 int radix_sort_pairs(u64 *keys_a, u64 *keys_b, u32 *idx_a, u32 *idx_b, size_t n, sort_scratch &sc, cudaStream_t st,
                      u64 **keys_out, u32 **idx_out)
 {

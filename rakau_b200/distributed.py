@@ -64,23 +64,37 @@ class ShardedTree:
             amax = torch.zeros(1, dtype=torch.float64, device=self.dev)
         dist.all_reduce(amax, op=dist.ReduceOp.MAX)
         box = deduce_box(float(amax.item()), self.fp)
-        # 1. local sort of the shard
-        self.local.sort_shard(x, y, z, m, n_loc, box)
-        codes, sx, sy, sz, sm, lp = self._sorted_arrays(self.local, n_loc)
-        gidx = lp + int(first_index)  # original (global) index of each locally sorted particle
+        partition = hasattr(self.local, "partition_shard") and self.world <= 256
+        if partition:
+            # 1. no local pre-sort: encode only; the splitter buckets are formed by ONE stable radix pass below
+            self.local.encode_shard(x, y, z, m, n_loc, box)
+            codes = torch.empty(n_loc, dtype=torch.int64, device=self.dev)
+            self.local.codes_device(codes)
+        else:
+            # 1. local sort of the shard
+            self.local.sort_shard(x, y, z, m, n_loc, box)
+            codes, sx, sy, sz, sm, lp = self._sorted_arrays(self.local, n_loc)
+            gidx = lp + int(first_index)  # original (global) index of each locally sorted particle
         self._ev.append(('local_sort', self._rec()))
-        # 2. splitters from regular samples (codes are < 2^63, so int64 order == unsigned order)
+        # 2. splitters from regular samples (codes are < 2^63, so int64 order == unsigned order); of the input order
+        # when the shard was only encoded - particles arrive unordered, so that is a random sample
         pos = (torch.arange(self.nsamp, device=self.dev, dtype=torch.int64) * max(n_loc - 1, 0)) // max(self.nsamp - 1, 1)
         samp = codes[pos] if n_loc else torch.full((self.nsamp,), 2 ** 62, dtype=torch.int64, device=self.dev)
         allsamp = torch.empty(self.nsamp * self.world, dtype=torch.int64, device=self.dev)
         dist.all_gather_into_tensor(allsamp, samp)
         allsamp, _ = torch.sort(allsamp)
-        split = allsamp[torch.arange(1, self.world, device=self.dev) * self.nsamp]
+        split = allsamp[torch.arange(1, self.world, device=self.dev) * self.nsamp].contiguous()
         self._ev.append(('splitters', self._rec()))
-        # 3. bucket exchange (one all-to-all per array; the arrays stay SoA and contiguous)
-        bounds = torch.searchsorted(codes, split, right=False)
-        bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=self.dev), bounds,
-                            torch.tensor([n_loc], dtype=torch.int64, device=self.dev)])
+        # 3. bucket exchange (the arrays stay SoA and contiguous)
+        if partition:
+            cnt = self.local.partition_shard(split)  # bucket r = codes in [split[r-1], split[r]), input order kept
+            codes, sx, sy, sz, sm, lp = self._sorted_arrays(self.local, n_loc)
+            gidx = lp + int(first_index)
+            bounds = torch.from_numpy(np.concatenate([[0], np.cumsum(cnt.astype(np.int64))])).to(self.dev)
+        else:
+            bounds = torch.searchsorted(codes, split, right=False)
+            bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=self.dev), bounds,
+                                torch.tensor([n_loc], dtype=torch.int64, device=self.dev)])
         send = (bounds[1:] - bounds[:-1])
         exchanged = self._push_a2a(send, bounds, (codes, sx, sy, sz, sm, gidx)) if self.cuda and self.world > 1 else None
         if exchanged is not None:
@@ -357,7 +371,8 @@ class ShardedTree:
             cuts += [int(v) for v in self.tree.crit_lower_bound(inner[i:i + 16])]
         return [0] + cuts + [int(self.tree.ncrit_nodes)]
 
-    def _ensure_cuts(self):
+    def ensure_cuts(self):
+        """Range cuts (self.cuts, self.cut_particles) for the current tree; called by acc_pot."""
         if self.cut_pidx is None or int(self.cut_pidx[-1]) != self.n or len(self.cut_pidx) != self.world + 1:
             # first evaluation: equal particle counts (tree.hpp:3147-3178)
             self.cut_pidx = [(r * self.n) // self.world for r in range(self.world)] + [self.n]
@@ -397,7 +412,7 @@ class ShardedTree:
         self._peer_flip ^= 1
         return self._peer[self._peer_flip]
 
-    def acc_pot(self, Q, theta, out=None, G=1.0, eps=0.0, exchange=True, chunks=(0.4, 0.7, 0.9)):
+    def acc_pot(self, Q, theta, out=None, G=1.0, eps=0.0, exchange=True, chunks=(0.4, 0.7, 0.9), host_out=None):
         """Evaluate this rank's Morton range; with exchange=True every rank ends with the full result (Morton order).
         Returns (info, outputs): outputs are `out` if given, else library-owned peer-memory buffers.
 
@@ -405,9 +420,11 @@ class ShardedTree:
         soon as a launch has finished, its contiguous output slice is pushed into every peer's buffer with
         copy-engine copies on a side stream (rk_device_copy_async) while the next launch occupies the SMs, so only the
         last tenth of the exchange is exposed. An NCCL kernel could not overlap: the traversal's persistent CTAs
-        fill every SM. Collective path (out given, or no peer memory): padded all-gather of the owned slices."""
+        fill every SM. Collective path (out given, or no peer memory): padded all-gather of the owned slices.
+        host_out: optional pinned host tensors (one per result, at least as long as this rank's particle range); the
+        slice of every finished launch is copied to them while the next launch runs (peer-memory path)."""
         torch, dist = self.torch, self.dist
-        self._ensure_cuts()
+        self.ensure_cuts()
         c0, c1 = int(self.cuts[self.rank]), int(self.cuts[self.rank + 1])
         nres = {0: 3, 1: 1, 2: 4}[Q]
         peer = self._peer_outputs(nres) if (out is None and exchange and self.world > 1 and self.cuda) else None
@@ -461,6 +478,10 @@ class ShardedTree:
                             "kernel_launches", "ms_kernel", "ms_total"):
                     info[key] += part[key]
             b, e = pcuts[k], pcuts[k + 1]
+            if e > b and host_out is not None:
+                with torch.cuda.stream(self._push[self.rank]):  # (this rank's own stream carries no peer pushes)
+                    for j in range(nres):
+                        host_out[j][b - pcuts[0]:e - pcuts[0]].copy_(out[j][b:e], non_blocking=True)
             if e > b:
                 for d in range(1, self.world):
                     r = (self.rank + d) % self.world  # staggered: at any time every rank receives from one peer

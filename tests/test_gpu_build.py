@@ -245,3 +245,42 @@ def test_digest_and_crit_lower_bound(oracle_mod, rk):
     assert "traverse_kernel" not in a.last_kernel()
     a.acc_pot(0, 0.75)
     assert a.last_kernel().startswith("traverse_kernel<float,Q=0,MAC=0")
+
+
+def test_partition_building_blocks_single_device(oracle_mod, rk):
+    """rk_tree_encode_shard + rk_tree_partition_shard (the sample sort without a local pre-sort): codes equal the
+    oracle's, every particle lands in the bucket of its code, buckets are contiguous and keep the input order (that is
+    what makes the receiving rank's stable sort reproduce the single-GPU order), sizes are reported."""
+    import torch
+    n = 300000
+    m, x, y, z = oracle_mod.plummer(n)
+    x[100:140] = x[50]  # equal codes across the shard
+    y[100:140] = y[50]
+    z[100:140] = z[50]
+    o = oracle_mod.OracleTree(x, y, z, m)
+    box = o.box_size
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(a).to(dev) for a in (x, y, z, m)]
+    t = rk.Octree()
+    t.set_stream(torch.cuda.current_stream().cuda_stream)
+    t.encode_shard(d[0], d[1], d[2], d[3], n, box)
+    codes = torch.empty(n, dtype=torch.int64, device=dev)
+    t.codes_device(codes)
+    inv = np.empty(n, dtype=np.int64)
+    inv[o.perm(0).astype(np.int64)] = np.arange(n)
+    want_codes = o.codes().astype(np.int64)[inv]  # the oracle's codes in input order
+    assert (codes.cpu().numpy() == want_codes).all()
+    split = torch.from_numpy(np.sort(want_codes)[[n // 5, n // 2, n // 2 + 7, 9 * n // 10]].copy()).to(dev)
+    cnt = t.partition_shard(split).astype(np.int64)
+    bucket = np.searchsorted(split.cpu().numpy(), want_codes, side="right")
+    assert (cnt == np.bincount(bucket, minlength=5)).all() and cnt.sum() == n
+    lp = torch.empty(n, dtype=torch.int32, device=dev)
+    t.perm_device(lp, rk.RK_LAST_PERM)
+    lp = lp.cpu().numpy().astype(np.int64)
+    assert (lp == np.argsort(bucket, kind="stable")).all()  # buckets contiguous, input order kept inside
+    t.codes_device(codes)
+    assert (codes.cpu().numpy() == want_codes[lp]).all()
+    cols = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(4)]
+    t.parts_device(*cols)
+    for got, a in zip(cols, (x, y, z, m)):
+        assert (got.cpu().numpy() == a[lp]).all()
