@@ -21,7 +21,8 @@ $(LIB): $(OBJS)
 	@mkdir -p rakau_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt
 
-oracle:
+# (oracle/_ref/libref_bridge.so links against the product library)
+oracle: $(LIB)
 	$(MAKE) -C oracle all
 
 clean:
