@@ -825,9 +825,14 @@ __device__ __forceinline__ void node_finalize(const dsum4 &s, u32 k, u32 b, u32 
     }
 }
 
-constexpr u32 PROPS_SMALL = 64; // nodes up to this size are reduced by 8 lanes, larger ones by a full warp
+#ifndef RK_PROPS_LANES
+#define RK_PROPS_LANES 1
+#endif
+constexpr int PROPS_LANES = RK_PROPS_LANES; // lanes per small node (86 % are leaves of ~5 particles: the kernel is bound by its
+                                             // dependent loads, so nodes in flight count - measured 16 / 8 / 4 / 2 / 1 lanes: 0.255 / 0.167 / 0.120 / 0.097 / 0.085 ms at 4 M)
+constexpr u32 PROPS_SMALL = 64; // nodes up to this size are reduced by PROPS_LANES lanes, larger ones by a full warp
 
-// 8 lanes per node (86 % of the nodes are leaves with <= 16 particles); larger nodes are queued for the
+// PROPS_LANES lanes per node (86 % of the nodes are leaves with <= 16 particles); larger nodes are queued for the
 // warp-per-node kernel.
 template <typename F>
 __global__ void __launch_bounds__(256)
@@ -837,15 +842,15 @@ __global__ void __launch_bounds__(256)
                             level_dims<F> ld, u64 *__restrict__ err, u32 *__restrict__ big_list,
                             u32 *__restrict__ big_count)
 {
-    const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const int gl = threadIdx.x & 7;
+    const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) / PROPS_LANES;
+    const int gl = threadIdx.x & (PROPS_LANES - 1);
     const bool in_range = k < n_nodes;
     uint4 nb = make_uint4(0, 0, 0, 0);
     if (in_range) {
         nb = nodeB[k];
     }
     const bool small = in_range && (nb.y - nb.x) <= PROPS_SMALL;
-    const dsum4 s = node_sum<F, 8>(p, chunks, nullptr, nb.x, nb.y, gl, small);
+    const dsum4 s = node_sum<F, PROPS_LANES>(p, chunks, nullptr, nb.x, nb.y, gl, small);
     if (gl == 0 && in_range) {
         if (small) {
             node_finalize<F>(s, k, nb.x, nb.w >> 8, codes, nodeA, node_delta, mac, ld, err);
@@ -1328,7 +1333,7 @@ void node_properties(build_arrays<F> &b, int mac, F box_size, cudaStream_t st)
         RK_CUDA_CHECK(cudaGetLastError());
         return;
     }
-    node_props_small_kernel<F><<<div_up(size_t(M) * 8, 256), 256, 0, st>>>(
+    node_props_small_kernel<F><<<div_up(size_t(M) * PROPS_LANES, 256), 256, 0, st>>>(
         b.psorted.p, b.codes, b.chunksum.p, b.nodeB.p, b.nodeA.p, b.node_delta.p, M, mac, ld, err, big_list, big_count); count_launch();
     node_props_big_kernel<F><<<148 * 4, 256, 0, st>>>(b.psorted.p, b.codes, b.chunksum.p, chunks2, b.nodeB.p, b.nodeA.p,
                                                      b.node_delta.p, mac, ld, err, big_list, big_count); count_launch();

@@ -1075,10 +1075,11 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                 h[7] = rs[RS_E0];
                 h[8] = rs[RS_PARTIAL];
             }
-            __threadfence();
+            __threadfence(); // every lane: its partial sums and frontier entries ...
             __syncwarp();
             if (lane == 0) {
-                h[2] = 1u; // ready
+                __threadfence(); // ... are ordered before the flag a thief polls (release)
+                h[2] = 1u;       // ready
                 __threadfence();
                 atomicAdd(p.steal_published, 1u);
             }
