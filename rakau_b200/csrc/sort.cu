@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(512) hist8_kernel(const u64 *__restrict__ keys
 // One pass: stable partition of the (key, idx) pairs by the digit at `shift`. status: one word per (tile, digit),
 // zeroed before the sort: bits 31:30 = 0 nothing yet, OS_AGG = count of this tile, OS_PREFIX = count of this and all
 // earlier tiles.
-__global__ void __launch_bounds__(SORT_THREADS)
+#ifndef RK_SORT_MINB
+#define RK_SORT_MINB 2
+#endif
+__global__ void __launch_bounds__(SORT_THREADS, RK_SORT_MINB)
     onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ idx_in, u64 *__restrict__ keys_out,
                     u32 *__restrict__ idx_out, size_t n, int shift, const u32 *__restrict__ ghist_pass,
                     u32 *__restrict__ status, u32 *__restrict__ tile_counter)
