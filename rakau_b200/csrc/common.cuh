@@ -191,7 +191,7 @@ struct build_arrays {
 constexpr int PROPS_CHUNK = 256;
 constexpr size_t PROPS_BOTTOMUP_MIN = size_t(8) << 20;
 #ifndef RK_TOPO_TILE
-#define RK_TOPO_TILE 256
+#define RK_TOPO_TILE 512
 #endif
 constexpr int TOPO_TILE = RK_TOPO_TILE; // particles per CTA of the node count / emit kernels
 
