@@ -203,6 +203,10 @@ RK_API const void *rk_tree_group_costs_device(rk_tree *t);
  * particle indices to the critical nodes of a rebuilt tree (the reference snaps its split the same way,
  * tree.hpp:3168-3178). */
 RK_API int rk_tree_crit_lower_bound(rk_tree *t, const uint64_t *particle_idx, size_t k, uint64_t *out);
+/* out[j][perm[i]] = in[j][i] for nres DEVICE arrays of nparts elements: results from the tree's Morton order to the
+ * original particle order (what the `_o` functions return, tree.hpp:3320-3330), asynchronously on the tree's stream.
+ * For callers that assembled Morton-order results themselves (the one-process-per-GPU evaluation). */
+RK_API int rk_tree_to_original_order(rk_tree *t, int nres, const void *const in[4], void *const out[4]);
 /* Order-independent 64-bit fingerprints of the device-resident arrays: codes, perm, particles (Morton order), node
  * topology (begin, end, first child, level | children), node properties (com, mass), critical node indices, critical
  * node first particles, (n_nodes << 32) ^ n_crit. Two trees with equal fingerprints are equal bit for bit (up to

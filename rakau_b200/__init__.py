@@ -37,7 +37,7 @@ SYMBOLS = [
     "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
     "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak", "rk_tree_set_option",
     "rk_tree_leapfrog_init", "rk_tree_leapfrog_step", "rk_tree_leapfrog_get", "rk_tree_encode_shard",
-    "rk_tree_partition_shard",
+    "rk_tree_partition_shard", "rk_tree_to_original_order",
 ]
 
 
@@ -139,6 +139,7 @@ def lib():
     L.rk_tree_crit_begin_at.argtypes = [vp, vp, sz, vp]
     L.rk_tree_crit_lower_bound.argtypes = [vp, vp, sz, vp]
     L.rk_tree_digest.argtypes = [vp, vp]
+    L.rk_tree_to_original_order.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     L.rk_tree_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     L.rk_tree_leapfrog_init.argtypes = [vp, vp, vp, vp, i32, dbl, dbl, dbl, i32]
     L.rk_tree_leapfrog_step.argtypes = [vp, dbl, C.POINTER(LeapfrogInfo)]
@@ -327,6 +328,14 @@ class Octree:
         idx = np.ascontiguousarray(particle_idx, dtype=np.uint64)
         out = np.empty(idx.size, dtype=np.uint64)
         self._check(self.L.rk_tree_crit_lower_bound(self.h, _ptr(idx), idx.size, _ptr(out)))
+        return out
+
+    def to_original_order(self, arrays, out):
+        """out[j][perm[i]] = arrays[j][i] for device arrays (torch tensors / pointers) in the tree's Morton order."""
+        n = len(arrays)
+        a = (C.c_void_p * 4)(*([_ptr(t) for t in arrays] + [None] * (4 - n)))
+        o = (C.c_void_p * 4)(*([_ptr(t) for t in out] + [None] * (4 - n)))
+        self._check(self.L.rk_tree_to_original_order(self.h, n, a, o))
         return out
 
     def digest(self):

@@ -1425,6 +1425,22 @@ public:
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
     }
 
+    // out[j][perm[i]] = in[j][i] on the device: results from Morton order to the original particle order
+    // (tree.hpp:3320-3330) for callers that assembled the Morton-order arrays themselves (sharded evaluation).
+    void to_original_order(int nres, const void *const in[4], void *const out[4])
+    {
+        use();
+        if (nres < 1 || nres > 4) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_to_original_order: 1 to 4 arrays");
+        }
+        for (int j = 0; j < nres; ++j) {
+            if (!in[j] || !out[j] || in[j] == out[j]) {
+                throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_to_original_order: distinct non-null device arrays");
+            }
+            launch_scatter_perm<F>(static_cast<const F *>(in[j]), m_b.perm.p, static_cast<F *>(out[j]), m_b.n, m_stream);
+        }
+        RK_CUDA_CHECK(cudaGetLastError());
+    }
     const char *last_kernel() const { return m_kernel_name; }
     void set_option(const std::string &name, long long value)
     {
@@ -2077,6 +2093,10 @@ int rk_tree_leapfrog_get(rk_tree *t, int what, void *a, void *b, void *c, int wh
 int rk_tree_set_option(rk_tree *t, const char *name, long long value)
 {
     return guarded(t, [&]() { RK_WITH(t, T.set_option(name ? name : "", value)); });
+}
+int rk_tree_to_original_order(rk_tree *t, int nres, const void *const in[4], void *const out[4])
+{
+    return guarded(t, [&]() { RK_WITH(t, T.to_original_order(nres, in, out)); });
 }
 int rk_tree_digest(rk_tree *t, uint64_t out[8])
 {

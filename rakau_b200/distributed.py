@@ -412,7 +412,19 @@ class ShardedTree:
         self._peer_flip ^= 1
         return self._peer[self._peer_flip]
 
-    def acc_pot(self, Q, theta, out=None, G=1.0, eps=0.0, exchange=True, chunks=(0.4, 0.7, 0.9), host_out=None):
+    def acc_pot(self, Q, theta, out=None, G=1.0, eps=0.0, exchange=True, chunks=(0.4, 0.7, 0.9), host_out=None,
+                ordered=False):
+        """ordered=True: after the exchange every rank re-orders the complete result from the Morton order to the
+        ORIGINAL (global) particle order, as the reference's `_o` functions do (tree.hpp:3320-3330); see _acc_pot."""
+        info, res = self._acc_pot(Q, theta, out=out, G=G, eps=eps, exchange=exchange, chunks=chunks, host_out=host_out)
+        if ordered:
+            assert exchange, "the original order needs the complete result"
+            dst = [self._persistent('ord%d' % j, self.n, self.dt) for j in range(len(res))]
+            self.tree.to_original_order([r[:self.n] for r in res], dst)
+            res = dst
+        return info, res
+
+    def _acc_pot(self, Q, theta, out=None, G=1.0, eps=0.0, exchange=True, chunks=(0.4, 0.7, 0.9), host_out=None):
         """Evaluate this rank's Morton range; with exchange=True every rank ends with the full result (Morton order).
         Returns (info, outputs): outputs are `out` if given, else library-owned peer-memory buffers.
 
@@ -547,10 +559,18 @@ class ShardedTree:
         single.acc_pot(Q, theta, G=G, eps=eps, out=ref, where=RK_DEVICE)
         acc_equal = all(bool(torch.equal(a[:n], b)) for a, b in zip(outs, ref))
         max_diff = max(float((a[:n] - b).abs().max().item()) for a, b in zip(outs, ref))
+        # ... and in the ORIGINAL particle order (tree.hpp:3320-3330): the single-GPU tree's own ordered evaluation
+        # against this rank's re-ordered copy of the sharded result
+        ref_o = [torch.empty(n, dtype=self.dt, device=self.dev) for _ in range(len(outs))]
+        single.acc_pot(Q, theta, G=G, eps=eps, out=ref_o, where=RK_DEVICE, ordered=True)
+        mine_o = self.tree.to_original_order([a[:n] for a in outs], [torch.empty_like(r) for r in ref_o])
+        ordered_equal = all(bool(torch.equal(a, b)) for a, b in zip(mine_o, ref_o))
+        acc_equal = acc_equal and ordered_equal
+        del ref_o, mine_o
         ok = torch.tensor([1 if (not differing and acc_equal) else 0], dtype=torch.int64, device=self.dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         single.close()
         return {"ok": bool(ok.item()), "nparts": n, "tree_arrays_differing": differing,
-                "accelerations_bit_equal": acc_equal, "max_abs_diff": max_diff,
+                "accelerations_bit_equal": acc_equal, "original_order_bit_equal": ordered_equal, "max_abs_diff": max_diff,
                 "what": "sharded tree fingerprints and gathered accelerations vs a single-GPU build + full evaluation "
                         "of the same particles on every rank"}

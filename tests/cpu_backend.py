@@ -82,6 +82,11 @@ class CpuOctree:
         b = np.append(self._begin, self.n)
         return b[np.asarray(idx, dtype=np.int64)].astype(np.uint64)
 
+    def to_original_order(self, arrays, out):
+        for a, o in zip(arrays, out):
+            o[torch.from_numpy(self._perm.astype(np.int64))] = a
+        return out
+
     def crit_lower_bound(self, particle_idx):
         return np.searchsorted(self._begin, np.asarray(particle_idx, dtype=np.int64), side="left").astype(np.uint64)
 

@@ -108,6 +108,9 @@ def _sharded_worker(rank, world, port, q):
     ok_resnap = all(int(begins[c]) >= pb and (c == 0 or int(begins[c - 1]) < pb) for c, pb in zip(st.cuts[1:-1], pidx2[1:-1]))
     ok_resnap &= [int(v) for v in st.cut_pidx] == pidx2
     ok_eval &= all(bool((o.numpy() == CpuOctree.expected(sorted_parts, j)).all()) for j, o in enumerate(out3))
+    # results in the ORIGINAL (global) particle order, as the reference's `_o` functions return them
+    _, out4 = st.acc_pot(0, 0.75, out=[torch.full((N,), float("nan")) for _ in range(3)], ordered=True)
+    ok_eval &= all(bool((o.numpy() == CpuOctree.expected(full, j)).all()) for j, o in enumerate(out4))
     tot = torch.tensor([info1["interactions"], info2["interactions"]], dtype=torch.int64)
     dist.all_reduce(tot)
     q.put((rank, ok_build, ok_eval and ok_resnap, cuts1, cuts2, imb, tot.tolist()))
