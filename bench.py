@@ -285,6 +285,22 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
+def strong_scaling_base(nparts, ms_per_step):
+    """The same workload on ONE GPU, from the committed N = 1 line (its `configs.strong_scaling_base_128M` block is
+    measured by every N = 1 run of this script with the same chunked generator): lets a reader form the strong-scaling
+    speed-up on equal work without mixing it with the 4 M headline workload."""
+    try:
+        path = os.path.join(ROOT, "profiles", "r02_bench_1gpu.json")
+        b = json.load(open(path))["configs"]["strong_scaling_base_128M"]
+        if int(b["nparts"]) != int(nparts):
+            return None
+        return {"n_gpus": 1, "ms_per_step": b["ms_per_step"], "ginteractions_per_s": b["ginteractions_per_s"],
+                "source": os.path.relpath(path, ROOT) + " configs.strong_scaling_base_128M",
+                "speedup_vs_1gpu": b["ms_per_step"] / ms_per_step}
+    except Exception:  # informational only
+        return None
+
+
 def median(v):
     return float(statistics.median(v))
 
@@ -617,6 +633,7 @@ def run_ours(args):
         line["ms_traverse_kernel_per_rank"] = [float(k.item()) for k in kall]
         line["build_note"] = ("ms_build = distributed sample sort (local sort, bucket exchange, bucket sort, gather) + "
                               "replicated topology/properties; build_phases_ms covers the replicated part only")
+        line["strong_scaling_base"] = strong_scaling_base(nparts, ms_per_step)
         line["parity_checked"] = bool(parity and parity.get("ok"))
         line["parity"] = parity
         line["perturbed_between_steps"] = bool(args.perturb)
