@@ -80,6 +80,22 @@ def test_benchmark_leapfrog_cli_validates_options(rk):
 
 
 @pytest.mark.gpu
+def test_benchmark_move_runs(rk):
+    """benchmark/benchmark_move.cpp (reference: benchmark/benchmark_move.cpp:44-76): evaluate, shift all particles
+    through update_particles_u, evaluate again. A uniform shift inside the fixed box leaves the forces unchanged up to
+    rounding, and both tree results agree with the direct sums printed beside them."""
+    subprocess.check_call(["make", "-C", BENCH], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(BENCH, "bin", "benchmark_move"), "--nparts", "200000", "--idx", "11", "--bsize",
+                        "400", "--mac_value", "0.5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    vec = [[float(v) for v in ln.split(",")] for ln in r.stdout.strip().splitlines() if ln.count(",") == 2]
+    assert len(vec) == 4
+    rel = lambda a, b: sum((u - v) ** 2 for u, v in zip(a, b)) ** 0.5 / sum(v * v for v in b) ** 0.5
+    assert rel(vec[0], vec[1]) < 2e-2 and rel(vec[2], vec[3]) < 2e-2
+    assert rel(vec[3], vec[1]) < 1e-3  # exact sums before / after the shift
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,nlines", [("benchmark_pot", 1), ("benchmark_acc_pot", 3)])
 def test_benchmark_pot_and_acc_pot_run(rk, name, nlines):
     """The printed tree result on particle --idx agrees with the printed direct sum (a smoke check of the programs; the
