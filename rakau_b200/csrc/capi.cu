@@ -757,11 +757,7 @@ public:
         }
         unsigned launches = 1;
         const bool pipelined = where == RK_HOST && !ordered && (pe - pb) >= (size_t(1) << 20);
-        const bool lists = prepare_lists(c1 - c0, (partial && where != RK_HOST) ? n * (c1 - c0) / C + 1 : pe - pb, NCHUNK);
         if (!pipelined) {
-            if (lists) {
-                attach_lists(p, c0, 0, 0., 1.);
-            }
             launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream, m_kernel_name);
             RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
             if (where == RK_HOST) {
@@ -812,9 +808,6 @@ public:
                 if (k != NCHUNK - 1) {
                     q.steal = nullptr; // the next launch fills the SMs this one leaves: only the last one has a tail
                 }
-                if (lists) {
-                    attach_lists(q, c0, k, double(pcut[k] - pb) / double(pe - pb), double(pcut[k + 1] - pb) / double(pe - pb));
-                }
                 launch_traverse<F>(q, Q, m_mac, m_sm_count, st, m_kernel_name);
                 RK_CUDA_CHECK(cudaEventRecord(m_chunk_ev[k], st));
                 ++launches;
@@ -842,11 +835,8 @@ public:
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[7], m_stream));
         RK_CUDA_CHECK(cudaStreamSynchronize(m_stream));
         const u32 *hw = reinterpret_cast<const u32 *>(m_hpin + 8);
-        if (hw[1] & 1u) {
+        if (hw[1]) {
             throw api_error(RK_ERR_RUNTIME, "Traversal stack overflow in the CUDA kernel");
-        }
-        if (lists) {
-            m_list_need = m_hpin[6]; // (bit 1 of hw[1]: a slice overflowed and the fused launch did the work)
         }
         m_costs_valid = true; // groups outside the evaluated ranges hold 0
         if (info) {
@@ -863,44 +853,6 @@ public:
         }
     }
 
-
-    // Arena + tables of the split evaluation for launches over nc critical nodes holding np particles in all. The arena
-    // holds 1.5 x what the previous evaluation produced (48 entries per particle when unknown) if that is at most a
-    // third of the free device memory; otherwise (and for fp64) the evaluation stays fused.
-    bool prepare_lists(size_t nc, size_t np, size_t nlaunch)
-    {
-        static const bool env_on = [] {
-            const char *e = std::getenv("RK_SPLIT_LISTS");
-            return e && e[0] == '1';
-        }();
-        if (sizeof(F) != 4 || !(m_split_lists < 0 ? env_on : m_split_lists != 0) || nc == 0) {
-            return false;
-        }
-        const u64 want = m_list_need ? m_list_need + m_list_need / 2 + (u64(1) << 22) : u64(np) * 48u;
-        if (want > m_list.cap) {
-            size_t free_b = 0, total_b = 0;
-            RK_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-            if (want * sizeof(u32) > (free_b + m_list.cap * sizeof(u32)) / 3) {
-                return false;
-            }
-            m_list.reserve(want);
-        }
-        m_list_off.reserve(trav_list_table_entries(nc) + 2 * nlaunch);
-        m_list_cnt.reserve(trav_list_table_entries(nc) + 2 * nlaunch);
-        return true;
-    }
-    // launch k of nlaunch over [c0k, c1k) of the range starting at c0: arena share [f0, f1) of the particles
-    void attach_lists(trav_params<F> &q, size_t c0, size_t k, double f0, double f1)
-    {
-        const u64 cap = m_list.cap, b = static_cast<u64>(double(cap) * f0) & ~u64(31),
-                  e = static_cast<u64>(double(cap) * f1) & ~u64(31);
-        q.list = m_list.p + b;
-        q.list_cap = e - b;
-        const size_t tb = 2 * (size_t(q.c0) - c0) + 2 * k;
-        q.list_off = m_list_off.p + tb;
-        q.list_cnt = m_list_cnt.p + tb;
-        q.list_fallback = 0;
-    }
 
     // ---- one process, several devices: the reference's `split` kwarg (tree.hpp:3147-3198) ---------------------------
     // split[0] is the CPU share of the reference; there is no CPU path here, so it is evaluated by the first
@@ -1494,8 +1446,6 @@ public:
     {
         if (name == "props_bottom_up") {
             m_b.props_bottom_up = value < 0 ? -1 : (value != 0);
-        } else if (name == "split_lists") {
-            m_split_lists = value < 0 ? -1 : (value != 0);
         } else {
             throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_set_option: unknown option '" + name + "'");
         }
@@ -1840,12 +1790,6 @@ private:
     size_t m_range_groups = 0;
     dbuf<u64> m_group_cost, m_counters;
     dbuf<u32> m_work, m_steal;
-    // split evaluation (traverse.cu): interaction-list arena + launch-relative tables; entries the last evaluation
-    // produced (0: unknown); -1: RK_SPLIT_LISTS decides (default off), 0 / 1: rk_tree_set_option("split_lists")
-    dbuf<u32> m_list, m_list_cnt;
-    dbuf<u64> m_list_off;
-    u64 m_list_need = 0;
-    int m_split_lists = -1;
     dbuf<u64> m_ids_sorted; // partition_shard scratch
     bool m_costs_valid = false, m_have_inv = false, m_pending_check_encode = false;
     F m_pending_inv_box = F(0);

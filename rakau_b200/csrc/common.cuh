@@ -289,22 +289,7 @@ struct trav_params {
     // frontier size, phase-1 counters, first group, partial flag), zeroed before the launch, + their frontiers
     u32 *steal, *steal_front, *steal_published;
     u32 steal_k;
-    // Split evaluation (fp32; list == NULL: the fused kernel). A WALK launch writes every unit's interaction list - the
-    // accepted nodes (entry = node index) and the particles of the opened leaves (entry = 0x80000000 | particle
-    // index) in the order the fused kernel would evaluate them - into the arena, each warp into its own slice; an
-    // EVALUATION launch then streams the lists. Tables are indexed relative to the launch: group g -> g - c0, the
-    // phase-1 list of the launch's run u -> (c1 - c0) + u. list_cnt == 0xffffffff: no phase-1 list for that run.
-    // counters[6] receives the entries produced (counted past an overflow); an overflowing slice sets bit 1 of *err,
-    // the evaluation launch then does nothing and a fused launch (list_fallback != 0) redoes the whole range.
-    u32 *list;
-    u64 list_cap;   // entries in the arena
-    u64 list_slice; // entries per warp of the walk launch (set by launch_traverse)
-    u64 *list_off;
-    u32 *list_cnt;
-    u32 list_fallback; // fused kernel: run only if bit 1 of *err is set
 };
-// entries of the two launch-relative tables for a launch over nc critical nodes
-inline size_t trav_list_table_entries(size_t nc) { return 2 * nc + 2; }
 constexpr unsigned TRAV_STEAL_SLOTS = 2048;
 // words per stolen frontier = the per-warp stack capacity of traverse.cu
 unsigned trav_stack_cap();

@@ -41,7 +41,6 @@
 #include "common.cuh"
 #include "scan.cuh"
 
-#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -53,9 +52,6 @@ namespace
 
 constexpr int TRAV_WARPS = 4;
 constexpr int TRAV_THREADS = TRAV_WARPS * 32;
-#ifndef RK_ACC_INPLACE
-#define RK_ACC_INPLACE 1
-#endif
 #ifndef RK_UNROLL
 #define RK_UNROLL 4
 #endif
@@ -89,9 +85,6 @@ constexpr int TRAV_THREADS = TRAV_WARPS * 32;
 #ifndef RK_BATCH_BIG
 #define RK_BATCH_BIG 128
 #endif
-#ifndef RK_WALK_CTAS
-#define RK_WALK_CTAS 6 // resident CTAs of the walk launch of the split evaluation (latency-bound: more warps, fewer registers)
-#endif
 #define RK_PRAGMA_(x) _Pragma(#x)
 #define RK_UNROLL_PRAGMA(n) RK_PRAGMA_(unroll n)
 // BATCH (template parameter of the kernel) = sources evaluated per consume step; the source ring holds 2 * BATCH
@@ -117,12 +110,6 @@ __device__ __forceinline__ void cp_async_vec4(double4 *dst, const double4 *src)
     cp_async_16(reinterpret_cast<char *>(dst) + 16, reinterpret_cast<const char *>(src) + 16);
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // MUFU.RSQ without the denormal pre/post-scaling of rsqrtf() (a squared distance below 1e-38 is not a
 // meaningful input; it flushes to zero exactly like a coincident pair).
@@ -261,17 +248,6 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
     return d;
 }
 
-// c += a * b with the accumulator tied to one register pair ("+l"): with a separate output operand ptxas ends every
-// unrolled trip with one MOV per accumulator half to bring the sums back to the registers of the loop header.
-__device__ __forceinline__ void fma2_acc(u64 &c, u64 a, u64 b)
-{
-#if RK_ACC_INPLACE
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
-#else
-    c = fma2(a, b, c);
-#endif
-}
-
 // NP pairs of target slots (slots 2k and 2k+1 of the tile; SINGLE: one slot, paired with itself and the upper half
 // discarded) against the sources src[jb, je).
 template <int Q, int NP, bool SINGLE, bool SELF>
@@ -320,12 +296,12 @@ RK_UNROLL_PRAGMA(RK_UNROLL)
             const u64 inv = pk2(ia, ib);
             if (Q != 1) {
                 const u64 ms = mul2(sm, mul2(mul2(inv, inv), inv));
-                fma2_acc(ax[k], dx, ms);
-                fma2_acc(ay[k], dy, ms);
-                fma2_acc(az[k], dz, ms);
+                ax[k] = fma2(dx, ms, ax[k]);
+                ay[k] = fma2(dy, ms, ay[k]);
+                az[k] = fma2(dz, ms, az[k]);
             }
             if (Q != 0) {
-                fma2_acc(ap[k], sm, inv);
+                ap[k] = fma2(sm, inv, ap[k]);
             }
         }
     }
@@ -411,20 +387,12 @@ __host__ __device__ constexpr u32 acc_entries(u32 tmax)
     return tmax <= 128u ? 2u * tmax : tmax + tmax / 2u;
 #endif
 }
-// Launch modes of traverse_kernel. FUSED: walk and evaluation in one launch (every configuration). The split evaluation
-// (fp32, trav_params::list) runs the same code twice: a WALK launch that appends to interaction lists where the
-// fused kernel fills its source ring - no ring, no accumulators, 80 registers: 6 CTAs per SM hide the node-fetch
-// latency the 4 CTAs of the fused kernel cannot - and an EVAL launch that refills the ring from the lists instead
-// of walking, so that all its warps sit in the FMA-bound loops all the time.
-enum { MODE_FUSED = 0, MODE_WALK = 1, MODE_EVAL = 2 };
-template <typename F, int MODE = MODE_FUSED>
+template <typename F>
 __host__ __device__ constexpr size_t warp_smem_bytes(u32 tmax, u32 LCAP)
 {
-    // ring + staged targets + accumulators + stack + queues (the walk launch: a 32-entry scratch block instead of the
-    // ring, no accumulators)
-    return size_t(MODE == MODE_WALK ? 32u : LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>)
-           + size_t(MODE == MODE_WALK ? 0u : acc_entries(tmax)) * sizeof(vec4<F>) + size_t(STACK_CAP) * 4 + 32 * 4 /*lq_incl*/
-           + 32 * 4 /*lq_base*/ + 16 * 4 /*run state*/;
+    // ring + staged targets + accumulators + stack + queues
+    return size_t(LCAP) * sizeof(vec4<F>) + size_t(tmax) * sizeof(vec4<F>) + size_t(acc_entries(tmax)) * sizeof(vec4<F>)
+           + size_t(STACK_CAP) * 4 + 32 * 4 /*lq_incl*/ + 32 * 4 /*lq_base*/ + 16 * 4 /*run state*/;
 }
 
 // First index j in [a, b) with arr[j] >= x, else b; the 32 lanes probe 32 positions per round (monotone array).
@@ -459,30 +427,17 @@ __device__ __forceinline__ u32 warp_lower_bound(const u32 *__restrict__ arr, u32
 // the additions differs. On the 4M Plummer tree this removes 47 % of the node visits and 43 % of the interactions
 // come from phase 1 (tests/studies/two_phase_walk_study.py).
 // (fp64: the double4 rings and accumulators let 3 CTAs fit in shared memory, so the kernel may use 168 registers)
-template <typename F, int Q, int MAC, int BATCH_, int MODE = MODE_FUSED>
-__global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS : (sizeof(F) == 8 ? RK_F64_CTAS : RK_CTAS))
-    traverse_kernel(const trav_params<F> p)
+template <typename F, int Q, int MAC, int BATCH_>
+__global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : RK_CTAS) traverse_kernel(const trav_params<F> p)
 {
     constexpr u32 BATCH = BATCH_, LCAP = 2 * BATCH_;
-    constexpr u32 LIST_NONE = 0xffffffffu, LIST_PART = 0x80000000u;
-    if (MODE == MODE_FUSED && p.list_fallback && !(*static_cast<volatile u32 *>(p.err) & 2u)) {
-        return; // fallback launch of the split evaluation: the lists fitted, there is nothing to redo
-    }
-    if (MODE == MODE_EVAL && (*static_cast<volatile u32 *>(p.err) & 2u)) {
-        return; // a slice of the arena overflowed: the fused launch that follows evaluates the range
-    }
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *base = smem_raw + size_t(warp) * warp_smem_bytes<F, MODE>(p.tmax, LCAP);
+    unsigned char *base = smem_raw + size_t(warp) * warp_smem_bytes<F>(p.tmax, LCAP);
     vec4<F> *ring = reinterpret_cast<vec4<F> *>(base);
-    vec4<F> *tgt = ring + (MODE == MODE_WALK ? 32u : LCAP);
+    vec4<F> *tgt = ring + LCAP;
     vec4<F> *acc = tgt + p.tmax;
-    u32 *stack = reinterpret_cast<u32 *>(acc + (MODE == MODE_WALK ? 0u : acc_entries(p.tmax)));
-    // walk launch: this warp's slice of the arena
-    const u64 slice_lo = MODE == MODE_WALK ? (u64(blockIdx.x) * TRAV_WARPS + u64(warp)) * p.list_slice : 0u;
-    const u64 slice_hi = slice_lo + (MODE == MODE_WALK ? p.list_slice : 0u);
-    u64 wpos = slice_lo, produced = 0u;
-    bool ovf = false;
+    u32 *stack = reinterpret_cast<u32 *>(acc + acc_entries(p.tmax));
     const u32 rr_cap = acc_entries(p.tmax) / 32u;              // accumulator slots per lane (one group)
     const u32 rr_cap1 = (p.tmax + acc_entries(p.tmax)) / 32u; // phase 1: the staged-target area holds accumulators too
     // the run's frontier lives at the top of the stack array and grows downwards: front(i) = stack_top[-i]
@@ -492,7 +447,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
     // state of the run this warp is attached to: kept in shared memory, it is only needed between stages
     // (registers are what limits the evaluation loop)
     u32 *rs = lq_base + 32;
-    enum { RS_J0, RS_J1, RS_E0, RS_NG, RS_SLOT, RS_FCOUNT, RS_MAC1, RS_ACC1, RS_P2P1, RS_PARTIAL, RS_NEED_PH1, RS_GI, RS_UNIT };
+    enum { RS_J0, RS_J1, RS_E0, RS_NG, RS_SLOT, RS_FCOUNT, RS_MAC1, RS_ACC1, RS_P2P1, RS_PARTIAL, RS_NEED_PH1, RS_GI };
     const u32 ltm = lanemask_lt();
     const F eps2 = p.eps2;
     const u32 W = p.window;
@@ -536,13 +491,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                     ng = e1 > e0 ? e1 - e0 : 0u;
                 }
                 // phase 1 is skipped for a single group: its walk then starts at the root
-                bool need_ph1 = j1 - j0 > 1u && ng != 0u;
-                if (MODE == MODE_EVAL && need_ph1) {
-                    need_ph1 = p.list_cnt[(p.c1 - p.c0) + u] != LIST_NONE; // (the walk gave up on phase 1: no list)
-                }
-                if (MODE == MODE_WALK && W && !need_ph1 && lane == 0) {
-                    p.list_cnt[(p.c1 - p.c0) + u] = LIST_NONE;
-                }
+                const bool need_ph1 = j1 - j0 > 1u && ng != 0u;
                 if (n_units - 1u - u < ksteal) {
                     if (need_ph1) {
                         slot = n_units - 1u - u; // published after phase 1
@@ -568,7 +517,6 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                     rs[RS_PARTIAL] = 0u;
                     rs[RS_NEED_PH1] = need_ph1 ? 1u : 0u;
                     rs[RS_GI] = 0u;
-                    rs[RS_UNIT] = u;
                 }
                 __syncwarp();
             }
@@ -656,15 +604,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
         // ... and, for the quick rejection test of the MAC, the group's (approximate) support points along the 8
         // diagonal directions: cand_pos byte q = index of the target maximising (+x, sy*y, sz*z), q = 2*(sy<0)+(sz<0);
         // cand_neg byte q = the same for (-x, sy*y, sz*z).
-        F blo[3] = {F(0), F(0), F(0)}, bhi[3] = {F(0), F(0), F(0)};
-        u32 cand_pos = 0u, cand_neg = 0u;
-        if constexpr (MODE == MODE_EVAL) {
-            if (staged) {
-                for (u32 i = lane; i < T; i += 32) {
-                    tgt[i] = gsrc[i];
-                }
-            }
-        } else {
+        F blo[3], bhi[3];
+        u32 cand_pos, cand_neg;
+        {
             u32 kmax[4] = {0u, 0u, 0u, 0u}, kmin[4] = {0u, 0u, 0u, 0u};
             F lo0 = F(INFINITY), lo1 = F(INFINITY), lo2 = F(INFINITY), hi0 = -F(INFINITY), hi1 = -F(INFINITY),
               hi2 = -F(INFINITY);
@@ -727,7 +669,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
         // phase 1 writes partial sums for the targets of this launch only
         const u32 fb = ph1 ? p.crit_begin[rs[RS_E0]] : 0u, fe = ph1 ? p.crit_begin[rs[RS_E0] + rs[RS_NG]] : 0u;
         vec4<F> *acc_lane = (ph1 ? tgt : acc) + lane; // phase 1 reads its targets from global memory (L1)
-        for (u32 t0 = 0; t0 < T; t0 += (MODE == MODE_WALK ? T : 32u * cap)) { // (the walk does not depend on the pass)
+        for (u32 t0 = 0; t0 < T; t0 += 32u * cap) {
             const u32 tc = (T - t0 < 32u * cap) ? (T - t0) : 32u * cap;
             // Slice the warp: P lanes per slice, S = 32/P slices, rr target slots per lane; minimise rr * P >= tc.
             // Cost of a choice = slots + half a slot per lane when rr is odd: the fp32 loop evaluates two slots per
@@ -744,10 +686,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                 }
             }
             const u32 P = 1u << lp, sl = static_cast<u32>(lane) >> lp, tl = static_cast<u32>(lane) & (P - 1u);
-            if constexpr (MODE != MODE_WALK) {
-                for (u32 k = 0; k < rr; ++k) {
-                    acc_lane[32u * k] = make_vec4<F>(F(0), F(0), F(0), F(0));
-                }
+            for (u32 k = 0; k < rr; ++k) {
+                acc_lane[32u * k] = make_vec4<F>(F(0), F(0), F(0), F(0));
             }
 
             // phase 1 starts at the root; a group starts at the run's frontier (the root when there was no phase 1)
@@ -762,66 +702,13 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
             }
             __syncwarp();
 
-            if constexpr (MODE == MODE_EVAL) {
-                // ---- the sources come from the unit's list, in batches of BATCH: the gather of batch b + 1 (list
-                // entries -> cp.async of the nodes' centres of mass / the particles into the other half of the ring)
-                // is in flight while batch b is evaluated ----
-                const u32 ui = ph1 ? (p.c1 - p.c0) + rs[RS_UNIT] : g - p.c0;
-                const u32 cnt = p.list_cnt[ui];
-                const u32 *lst = p.list + p.list_off[ui];
-                auto gather = [&](u32 b, u32 half) {
-                    const u32 nb_ = cnt - b < BATCH ? cnt - b : BATCH;
-                    for (u32 i = lane; i < nb_; i += 32) {
-                        const u32 e = __ldcs(lst + b + i);
-                        cp_async_vec4(&ring[half * BATCH + i], (e & LIST_PART) ? p.parts + (e & ~LIST_PART) : p.nodeA + e);
-                    }
-                    cp_async_commit();
-                };
-                if (cnt) {
-                    gather(0u, 0u);
-                }
-                for (u32 b = 0, half = 0; b < cnt; b += BATCH, half ^= 1u) {
-                    const u32 ne = cnt - b < BATCH ? cnt - b : BATCH;
-                    if (b + BATCH < cnt) {
-                        gather(b + BATCH, half ^ 1u);
-                        cp_async_wait_group<1>();
-                    } else {
-                        cp_async_wait_group<0>();
-                    }
-                    __syncwarp();
-                    eval_slots_packed<Q, false>(reinterpret_cast<const float4 *>(ring + half * BATCH), ne, sl, 5u - lp, eps2,
-                                                reinterpret_cast<const float4 *>(tpos), T, t0 + tl, P, rr,
-                                                reinterpret_cast<float4 *>(acc_lane));
-                    __syncwarp();
-                }
-            } else
             for (;;) {
                 // ---------------- produce: fill the ring until >= 32 sources or the walk is over -------------
-                while ((MODE == MODE_WALK || lcount < BATCH) && !done) {
+                while (lcount < BATCH && !done) {
                     if (lq_done < lq_total) {
                         // copy more particles of the rejected leaves into the ring
                         const u32 room = LCAP - lcount, rem = lq_total - lq_done;
-                        const u32 chunk = MODE == MODE_WALK ? rem : (rem < room ? rem : room);
-                        if constexpr (MODE == MODE_WALK) {
-                            // (walk launch: their indices go to the list, all at once)
-                            ovf = ovf || wpos + lcount + chunk > slice_hi;
-                            for (u32 f = lq_done + lane; f < lq_done + chunk; f += 32) {
-                                int lo = 0;
-#pragma unroll
-                                for (int st = 16; st > 0; st >>= 1) {
-                                    if (lq_incl[lo + st - 1] <= f) {
-                                        lo += st;
-                                    }
-                                }
-                                if (!ovf) {
-                                    p.list[wpos + lcount + (f - lq_done)] = LIST_PART | (lq_base[lo] + f);
-                                }
-                            }
-                            __syncwarp();
-                            lcount += chunk;
-                            lq_done += chunk;
-                            continue;
-                        }
+                        const u32 chunk = rem < room ? rem : room;
                         for (u32 f = lq_done + lane; f < lq_done + chunk; f += 32) {
                             int lo = 0;
 #pragma unroll
@@ -935,8 +822,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                             // the 32 lanes share the targets of ONE node at a time (broadcast LDS.128 per node)
                             const u32 m_need = __ballot_sync(FULL, need);
                             const u32 n_need = __popc(m_need), my_slot = __popc(m_need & ltm);
-                            // a free 32-entry block (lcount < BATCH here; the walk launch has nothing else there)
-                            vec4<F> *amb = ring + (MODE == MODE_WALK ? 0u : ((lhead + BATCH) & (LCAP - 1)));
+                            vec4<F> *amb = ring + ((lhead + BATCH) & (LCAP - 1)); // a free 32-entry block (lcount < BATCH here)
                             if (need) {
                                 amb[my_slot] = make_vec4<F>(na.x, na.y, na.z, mac_lh);
                             }
@@ -1017,13 +903,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                             fcount += fover ? 0u : __popc(m_fr);
                         }
                     }
-                    // accepted nodes -> ring (walk launch: -> list)
-                    if constexpr (MODE == MODE_WALK) {
-                        ovf = ovf || wpos + lcount + 32u > slice_hi;
-                        if (accept && !ovf) {
-                            p.list[wpos + lcount + __popc(m_acc & ltm)] = k;
-                        }
-                    } else if (accept) {
+                    // accepted nodes -> ring
+                    if (accept) {
                         ring[(lhead + lcount + __popc(m_acc & ltm)) & (LCAP - 1)] = na;
                     }
                     lcount += __popc(m_acc);
@@ -1054,7 +935,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                         done = true;
                     }
                 }
-                if (MODE == MODE_WALK || lcount == 0u || fover) {
+                if (lcount == 0u || fover) {
                     break;
                 }
                 // ---------------- consume: evaluate up to 32 sources (the only ring call site) ----------------
@@ -1075,20 +956,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                 lcount -= ne;
             }
             if (overflow && lane == 0) {
-                atomicOr(p.err, 1u);
-            }
-            if constexpr (MODE == MODE_WALK) {
-                // the unit's list is complete (a phase 1 that ran out of frontier space leaves none)
-                const u32 ui = ph1 ? (p.c1 - p.c0) + rs[RS_UNIT] : g - p.c0;
-                const bool none = ph1 && fover;
-                if (lane == 0) {
-                    p.list_off[ui] = wpos;
-                    p.list_cnt[ui] = none ? LIST_NONE : (ovf ? 0u : lcount);
-                }
-                if (!none) {
-                    produced += lcount;
-                    wpos += ovf ? 0u : lcount;
-                }
+                atomicExch(p.err, 1u);
             }
             if (ph1) {
                 cp_async_wait_all();
@@ -1109,7 +977,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                     rs[RS_P2P1] = n_p2p;
                 }
                 __syncwarp();
-            } else if constexpr (MODE != MODE_WALK) {
+            } else {
                 // self interactions inside the group, tree.hpp:2073-2321 (sources = the group's own particles)
                 if constexpr (sizeof(F) == 4 && RK_PACKED) {
                     eval_slots_packed<Q, true>(reinterpret_cast<const float4 *>(staged ? tgt : gsrc), T, sl, 5u - lp, eps2,
@@ -1125,7 +993,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
             // Combine the slices' partial sums (fixed shuffle tree: deterministic). Phase 1 parks the run's partial
             // sums in the output arrays; a group adds them to its own, applies G as one final multiply
             // (tree.hpp:2986-3002) and writes out (3004-3007).
-            for (u32 k = 0; MODE != MODE_WALK && k < rr; ++k) {
+            for (u32 k = 0; k < rr; ++k) {
                 vec4<F> a = acc_lane[32u * k];
                 for (u32 o = P; o < 32u; o <<= 1) {
                     a.x += __shfl_xor_sync(FULL, a.x, o);
@@ -1175,7 +1043,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
                     }
                 }
             }
-            if (MODE != MODE_EVAL && !ph1 && t0 == 0 && lane == 0) {
+            if (!ph1 && t0 == 0 && lane == 0) {
                 const u32 t_mac = n_mac + rs[RS_MAC1], t_acc = n_acc + rs[RS_ACC1], t_p2p = n_p2p + rs[RS_P2P1];
                 if (p.group_cost) {
                     p.group_cost[g] = u64(T) * (u64(t_p2p) + t_acc + u64(T) - 1u);
@@ -1217,16 +1085,6 @@ __global__ void __launch_bounds__(TRAV_THREADS, MODE == MODE_WALK ? RK_WALK_CTAS
             }
             __syncwarp();
         }
-        }
-    }
-    if constexpr (MODE == MODE_WALK) {
-        if (lane == 0) {
-            if (p.counters) {
-                atomicAdd(p.counters + 6, produced); // what the arena must hold (counted past an overflow)
-            }
-            if (ovf) {
-                atomicOr(p.err, 2u);
-            }
         }
     }
 }
@@ -1338,88 +1196,9 @@ int trav_occupancy(u32 tmax, size_t &smem)
     return per_sm;
 }
 
-// Split evaluation (fp32): walk launch -> evaluation launch -> conditional fused launch, all on `st`. Returns false when
-// the arena is too small to be worth it (the caller then launches the fused kernel as usual).
-template <int Q, int MAC>
-bool launch_split(const trav_params<float> &p, int sm_count, cudaStream_t st, char *name)
-{
-    constexpr int BIG = RK_BATCH_BIG;
-    auto kw = traverse_kernel<float, 0, MAC, BIG, MODE_WALK>;
-    auto ke = traverse_kernel<float, Q, 0, BIG, MODE_EVAL>; // (the evaluation never tests a MAC)
-    const size_t smem_w = warp_smem_bytes<float, MODE_WALK>(p.tmax, 2 * BIG) * TRAV_WARPS,
-                 smem_e = warp_smem_bytes<float, MODE_EVAL>(p.tmax, 2 * BIG) * TRAV_WARPS;
-    int occ_w = 0, occ_e = 0;
-    if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_w)) != cudaSuccess
-        || cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_e)) != cudaSuccess
-        || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, kw, TRAV_THREADS, smem_w) != cudaSuccess
-        || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, ke, TRAV_THREADS, smem_e) != cudaSuccess || occ_w < 1
-        || occ_e < 1) {
-        cudaGetLastError();
-        return false;
-    }
-    const u32 need = (p.c1 - p.c0 + TRAV_WARPS - 1) / TRAV_WARPS;
-    const u32 grid_w = std::min<u32>(static_cast<u32>(sm_count * occ_w), need),
-              grid_e = std::min<u32>(static_cast<u32>(sm_count * occ_e), need);
-    if (grid_w == 0) {
-        return true;
-    }
-    trav_params<float> q = p;
-    q.list_slice = p.list_cap / (u64(grid_w) * TRAV_WARPS);
-    if (q.list_slice < 8192u) {
-        return false;
-    }
-    auto reset = [&]() {
-        RK_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(u32), st));
-        if (p.steal) {
-            RK_CUDA_CHECK(cudaMemsetAsync(p.steal, 0, size_t(p.steal_k) * 16 * sizeof(u32), st));
-            RK_CUDA_CHECK(cudaMemsetAsync(p.steal_published, 0, sizeof(u32), st));
-        }
-    };
-    static const int stage = std::getenv("RK_SPLIT_DEBUG") ? std::atoi(std::getenv("RK_SPLIT_DEBUG")) : 0; // timing experiments
-    kw<<<grid_w, TRAV_THREADS, smem_w, st>>>(q);
-    if (stage == 1) {
-        return true;
-    }
-    reset();
-    ke<<<grid_e, TRAV_THREADS, smem_e, st>>>(q);
-    if (stage == 2) {
-        return true;
-    }
-    reset();
-    // an overflowing arena slice (bit 1 of *err) turns the evaluation launch into a no-op and this one into the
-    // whole evaluation; the walk launch has already done the bookkeeping
-    q.list = nullptr;
-    q.list_fallback = 1u;
-    q.counters = nullptr;
-    q.group_cost = nullptr;
-    size_t smem_f = 0;
-    const int occ_f = trav_occupancy<float, Q, MAC, BIG>(p.tmax, smem_f);
-    if (occ_f < 1) {
-        throw cuda_error(1, "the traversal kernel does not fit on this device");
-    }
-    traverse_kernel<float, Q, MAC, BIG><<<std::min<u32>(static_cast<u32>(sm_count * occ_f), need), TRAV_THREADS, smem_f, st>>>(q);
-    count_launch(3);
-    RK_CUDA_CHECK(cudaGetLastError());
-    if (name) {
-        std::snprintf(name, 96, "traverse_kernel<float,Q=%d,MAC=%d,BATCH=%d> split walk(%d/SM)+eval(%d/SM) window=%u", Q, MAC,
-                      BIG, occ_w, occ_e, p.window);
-    }
-    static const bool debug = std::getenv("RK_DEBUG_LAUNCH") != nullptr;
-    if (debug) {
-        std::fprintf(stderr, "[rk] split: walk %u CTAs (%d/SM, %zu B), eval %u CTAs (%d/SM, %zu B), slice %llu entries\n", grid_w,
-                     occ_w, smem_w, grid_e, occ_e, smem_e, q.list_slice);
-    }
-    return true;
-}
-
 template <typename F, int Q, int MAC>
 void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *name)
 {
-    if constexpr (sizeof(F) == 4) {
-        if (p.list && launch_split<Q, MAC>(p, sm_count, st, name)) {
-            return;
-        }
-    }
     // batches of BIG sources (fp32: 128 at 4 CTAs/SM and 128 registers - measured 2.6 % faster at ncrit 128 and 7 % at
     // ncrit 256 than 64 at 5 CTAs/SM and 96 registers; fp64: 64) unless the larger ring costs a resident CTA
     constexpr int BIG = sizeof(F) == 4 ? RK_BATCH_BIG : 64;
