@@ -612,7 +612,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "Ginteractions/s", "ms_per_step": e2e_tot_ms / args.steps,
                 "h2d_bytes_per_step": 16 * count, "d2h_bytes_per_step": state["d2h"],
                 "pageable_host_buffers_ms_per_step": pageable_ms,
-                "note": "per rank: its input shard in, the output slice it owns out" if world > 1 else "rk_tree_build + rk_tree_acc_pot with pinned HOST buffers: all inputs in, all outputs out"},
+                "note": "per rank: its input shard in, the output slice it owns out" if world > 1 else "rk_tree_build + rk_tree_acc_pot with pinned HOST buffers: all inputs copied in, all outputs written into the host buffers by the traversal kernel (mapped memory, no copy behind the launch)"},
         "gpu_launches": int(launches), "clocks": clk,
         "vs_published_ms": {"note": "reference README traversal-only times, other hardware", "v100_ms": 95,
                             "xeon6148x2_ms": 82, "ours_traverse_ms": k_ms},

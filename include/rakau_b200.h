@@ -110,7 +110,10 @@ RK_API const char *rk_create_error(void);
 RK_API int rk_tree_set_stream(rk_tree *t, void *cuda_stream);
 RK_API int rk_tree_synchronize(rk_tree *t);
 /* Tuning switches that never change results beyond the documented tolerances. "props_bottom_up": node properties
- * bottom-up (1: every particle read once, one launch per level), top-down (0) or chosen by size (-1, the default). */
+ * bottom-up (1: every particle read once, one launch per level), top-down (0) or chosen by size (-1, the default).
+ * "zero_copy_out" (default 1): unordered results for host buffers in PINNED memory (cudaHostAlloc / cudaHostRegister)
+ * are written by the traversal kernel straight into those buffers, with no device-to-host copy behind the launch;
+ * 0 = always copy. Pageable host buffers and ordered outputs are always copied. */
 RK_API int rk_tree_set_option(rk_tree *t, const char *name, long long value);
 
 /* ---- construction: construct_impl, tree.hpp:1329-1487 ------------------------------------------------ */

@@ -756,11 +756,28 @@ public:
             pe = be[1];
         }
         unsigned launches = 1;
-        const bool pipelined = where == RK_HOST && !ordered && (pe - pb) >= (size_t(1) << 20);
+        // Host outputs in Morton order that live in pinned (mapped) memory: the kernel writes the final results straight
+        // into the caller's buffers - ONE launch with its work-stealing tail and no device-to-host copy behind it.
+        bool zero_copy = where == RK_HOST && !ordered && m_zero_copy_out != 0;
+        for (int j = 0; zero_copy && j < nres; ++j) {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, out[j]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                zero_copy = false;
+            } else {
+                p.outf[j] = static_cast<F *>(at.devicePointer);
+            }
+        }
+        if (!zero_copy) {
+            for (int j = 0; j < 4; ++j) {
+                p.outf[j] = nullptr;
+            }
+        }
+        const bool pipelined = !zero_copy && where == RK_HOST && !ordered && (pe - pb) >= (size_t(1) << 20);
         if (!pipelined) {
             launch_traverse<F>(p, Q, m_mac, m_sm_count, m_stream, m_kernel_name);
             RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[6], m_stream));
-            if (where == RK_HOST) {
+            if (where == RK_HOST && !zero_copy) {
                 for (int j = 0; j < nres; ++j) {
                     if (ordered) {
                         RK_CUDA_CHECK(
@@ -1446,6 +1463,8 @@ public:
     {
         if (name == "props_bottom_up") {
             m_b.props_bottom_up = value < 0 ? -1 : (value != 0);
+        } else if (name == "zero_copy_out") {
+            m_zero_copy_out = value != 0;
         } else {
             throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_set_option: unknown option '" + name + "'");
         }
@@ -1790,6 +1809,7 @@ private:
     size_t m_range_groups = 0;
     dbuf<u64> m_group_cost, m_counters;
     dbuf<u32> m_work, m_steal;
+    int m_zero_copy_out = 1; // rk_tree_set_option("zero_copy_out"): final results straight into pinned host outputs
     dbuf<u64> m_ids_sorted; // partition_shard scratch
     bool m_costs_valid = false, m_have_inv = false, m_pending_check_encode = false;
     F m_pending_inv_box = F(0);

@@ -278,6 +278,10 @@ struct trav_params {
     F mac_tab[NLEVELS]; // bh: dim2(level) * theta^-2 ; bh_geom: dim(level)
     F mac_value, eps2, G;
     F *out[4];
+    // where the FINAL results are written (streaming stores): NULL = out[j]. With host outputs in pinned memory this is
+    // the caller's buffer itself (mapped into the device's address space), so no device-to-host copy follows the launch;
+    // out[j] (device memory) still receives the partial sums phase 1 parks for phase 2, which are read back.
+    F *outf[4];
     const u32 *perm; // non-null: ordered outputs (scatter through perm)
     u64 *group_cost; // per critical node (nullable)
     u64 *counters;   // 5 x u64: mac_tests, accepted, p2p_pairs, self_pairs, sum T*accepted (nullable)

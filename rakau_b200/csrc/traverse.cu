@@ -1031,15 +1031,15 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                     }
                     const F tmass = tpos[i].w;
                     if (Q == 0 || Q == 2) {
-                        p.out[0][dst] = a.x * p.G;
-                        p.out[1][dst] = a.y * p.G;
-                        p.out[2][dst] = a.z * p.G;
+                        __stcs(p.outf[0] + dst, a.x * p.G);
+                        __stcs(p.outf[1] + dst, a.y * p.G);
+                        __stcs(p.outf[2] + dst, a.z * p.G);
                     }
                     if (Q == 1) {
-                        p.out[0][dst] = (-tmass * a.w) * p.G;
+                        __stcs(p.outf[0] + dst, (-tmass * a.w) * p.G);
                     }
                     if (Q == 2) {
-                        p.out[3][dst] = (-tmass * a.w) * p.G;
+                        __stcs(p.outf[3] + dst, (-tmass * a.w) * p.G);
                     }
                 }
             }
@@ -1255,8 +1255,12 @@ u32 trav_window(u32 tmax, size_t max_group)
 }
 
 template <typename F>
-void launch_traverse(const trav_params<F> &p, int Q, int mac, int sm_count, cudaStream_t st, char *name)
+void launch_traverse(const trav_params<F> &p_, int Q, int mac, int sm_count, cudaStream_t st, char *name)
 {
+    trav_params<F> p = p_;
+    for (int j = 0; j < 4; ++j) {
+        p.outf[j] = p.outf[j] ? p.outf[j] : p.out[j]; // final results go where the partial sums are unless told otherwise
+    }
 #define RK_DISPATCH(QQ, MM)                                                                                            \
     if (Q == QQ && mac == MM) {                                                                                        \
         launch_one<F, QQ, MM>(p, sm_count, st, name);                                                                  \

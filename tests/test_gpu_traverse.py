@@ -302,3 +302,37 @@ def test_pipelined_host_path_matches_device_path(oracle_mod, rk):
     lo = int(gh.crit_begin_at([3])[0])
     for j in range(4):
         assert (part[j][lo:] == host[j][lo:]).all() and np.isnan(part[j][:lo]).all()
+
+
+@pytest.mark.parametrize("Q", [0, 1, 2])
+def test_pinned_host_outputs_are_written_by_the_kernel(oracle_mod, rk, Q):
+    """Unordered outputs in PINNED host memory: the kernel writes the final results straight into the caller's buffers
+    (one launch, no device-to-host copy; the partial sums of phase 1 stay in device memory). Bit-identical to the
+    copied (pageable-buffer) route, for a full evaluation, for a range of critical nodes (nothing outside the range is
+    touched) and with the option switched off."""
+    import torch
+    n = (1 << 20) + 777
+    m, x, y, z = oracle_mod.plummer(n)
+    g = rk.Octree()
+    g.build(x, y, z, m)
+    nres = {0: 3, 1: 1, 2: 4}[Q]
+    ref = g.acc_pot(Q, 0.75, G=1.5, eps=0.001)  # numpy arrays: pageable, copied
+    assert g.eval_info.kernel_launches == 4
+    pinned = [torch.full((n,), float("nan"), dtype=torch.float32).pin_memory() for _ in range(nres)]
+    pn = [t.numpy() for t in pinned]
+    g.acc_pot(Q, 0.75, G=1.5, eps=0.001, out=pn)
+    assert g.eval_info.kernel_launches == 1
+    for j in range(nres):
+        assert (pn[j] == ref[j]).all(), j
+    C = g.ncrit_nodes
+    lo, hi = (int(v) for v in g.crit_begin_at([5, C - 7]))
+    for a in pn:
+        a[:] = np.nan
+    g.acc_pot(Q, 0.75, G=1.5, eps=0.001, out=pn, crit_range=(5, C - 7))
+    for j in range(nres):
+        assert (pn[j][lo:hi] == ref[j][lo:hi]).all() and np.isnan(pn[j][:lo]).all() and np.isnan(pn[j][hi:]).all()
+    g.set_option("zero_copy_out", 0)
+    g.acc_pot(Q, 0.75, G=1.5, eps=0.001, out=pn)
+    assert g.eval_info.kernel_launches == 4
+    for j in range(nres):
+        assert (pn[j] == ref[j]).all(), j
