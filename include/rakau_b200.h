@@ -115,6 +115,13 @@ RK_API int rk_tree_synchronize(rk_tree *t);
  * are written by the traversal kernel straight into those buffers, with no device-to-host copy behind the launch;
  * 0 = always copy. Pageable host buffers and ordered outputs are always copied. */
 RK_API int rk_tree_set_option(rk_tree *t, const char *name, long long value);
+/* Output mirrors: n <= 8 further copies of the output arrays (ptrs[4 * r + j] = array j of mirror r, device-accessible
+ * memory: another GPU's buffer mapped into this process, mapped pinned host memory) that every following
+ * rk_tree_acc_pot / rk_tree_acc_pot_range with DEVICE outputs writes as well, at the same indices, from inside the
+ * traversal kernel - the output exchange of a multi-GPU evaluation (each rank mirrors its range into its peers'
+ * buffers over NVLink while it computes; src/rakau_cuda.cu:492-527 copies each device's slice back afterwards instead).
+ * n = 0 switches it off. The caller orders the peers' reads after this call (a barrier across the ranks). */
+RK_API int rk_tree_set_output_mirrors(rk_tree *t, unsigned n, void *const *ptrs);
 
 /* ---- construction: construct_impl, tree.hpp:1329-1487 ------------------------------------------------ */
 /* Copies n particles (SoA x, y, z, m; host or device pointers) into the tree, deduces the box if

@@ -35,7 +35,7 @@ SYMBOLS = [
     "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak", "rk_device_copy_async",
     "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
     "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
-    "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak", "rk_tree_set_option",
+    "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak", "rk_tree_set_option", "rk_tree_set_output_mirrors",
     "rk_tree_leapfrog_init", "rk_tree_leapfrog_step", "rk_tree_leapfrog_get", "rk_tree_encode_shard",
     "rk_tree_partition_shard", "rk_tree_to_original_order",
 ]
@@ -141,6 +141,7 @@ def lib():
     L.rk_tree_digest.argtypes = [vp, vp]
     L.rk_tree_to_original_order.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     L.rk_tree_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    L.rk_tree_set_output_mirrors.argtypes = [vp, C.c_uint, C.POINTER(C.c_void_p)]
     L.rk_tree_leapfrog_init.argtypes = [vp, vp, vp, vp, i32, dbl, dbl, dbl, i32]
     L.rk_tree_leapfrog_step.argtypes = [vp, dbl, C.POINTER(LeapfrogInfo)]
     L.rk_tree_leapfrog_get.argtypes = [vp, i32, vp, vp, vp, i32]
@@ -207,6 +208,15 @@ class Octree:
 
     def synchronize(self):
         self._check(self.L.rk_tree_synchronize(self.h))
+
+    def set_output_mirrors(self, mirrors):
+        """mirrors: list (<= 8) of lists of integer device pointers / tensors, one per result array: further copies of
+        the outputs that the following device-output evaluations write from inside the kernel ([] = off)."""
+        flat = (C.c_void_p * (4 * max(len(mirrors), 1)))()
+        for r, arrs in enumerate(mirrors):
+            for j, a in enumerate(arrs):
+                flat[4 * r + j] = _ptr(a)
+        self._check(self.L.rk_tree_set_output_mirrors(self.h, len(mirrors), flat))
 
     def set_option(self, name, value):
         self._check(self.L.rk_tree_set_option(self.h, name.encode(), int(value)))

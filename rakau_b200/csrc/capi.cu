@@ -735,6 +735,17 @@ public:
                 p.out[j] = m_out[j].p;
             }
         }
+        if (where == RK_DEVICE && m_n_mirror) {
+            for (unsigned r = 0; r < m_n_mirror; ++r) {
+                for (int j = 0; j < nres; ++j) {
+                    if (!m_out_mirror[r][j]) {
+                        throw api_error(RK_ERR_INVALID_ARGUMENT, "Null output mirror pointer");
+                    }
+                    p.mirror[r][j] = m_out_mirror[r][j];
+                }
+            }
+            p.n_mirror = m_n_mirror;
+        }
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[4], m_stream));
         RK_CUDA_CHECK(cudaMemsetAsync(m_work.p, 0, 8 * sizeof(u32), m_stream));
         RK_CUDA_CHECK(cudaMemsetAsync(m_counters.p, 0, 8 * sizeof(u64), m_stream));
@@ -1459,6 +1470,21 @@ public:
         RK_CUDA_CHECK(cudaGetLastError());
     }
     const char *last_kernel() const { return m_kernel_name; }
+    // Copies of the output arrays (device-accessible: peer memory, mapped host memory) that the following evaluations
+    // with DEVICE outputs write as well, result by result, from inside the traversal kernel.
+    void set_output_mirrors(unsigned n, void *const *ptrs)
+    {
+        if (n > TRAV_MAX_MIRRORS || (n && !ptrs)) {
+            throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_set_output_mirrors: at most " + std::to_string(TRAV_MAX_MIRRORS)
+                                                         + " mirrors of 4 pointers each");
+        }
+        for (unsigned r = 0; r < n; ++r) {
+            for (int j = 0; j < 4; ++j) {
+                m_out_mirror[r][j] = static_cast<F *>(ptrs[4 * r + j]);
+            }
+        }
+        m_n_mirror = n;
+    }
     void set_option(const std::string &name, long long value)
     {
         if (name == "props_bottom_up") {
@@ -1809,6 +1835,8 @@ private:
     size_t m_range_groups = 0;
     dbuf<u64> m_group_cost, m_counters;
     dbuf<u32> m_work, m_steal;
+    F *m_out_mirror[TRAV_MAX_MIRRORS][4] = {};
+    unsigned m_n_mirror = 0; // rk_tree_set_output_mirrors
     int m_zero_copy_out = 1; // rk_tree_set_option("zero_copy_out"): final results straight into pinned host outputs
     dbuf<u64> m_ids_sorted; // partition_shard scratch
     bool m_costs_valid = false, m_have_inv = false, m_pending_check_encode = false;
@@ -2109,6 +2137,10 @@ int rk_tree_leapfrog_step(rk_tree *t, double dt, rk_leapfrog_info *info)
 int rk_tree_leapfrog_get(rk_tree *t, int what, void *a, void *b, void *c, int where)
 {
     return guarded(t, [&]() { RK_WITH(t, T.leapfrog_get(what, a, b, c, where)); });
+}
+int rk_tree_set_output_mirrors(rk_tree *t, unsigned n, void *const *ptrs)
+{
+    return guarded(t, [&]() { RK_WITH(t, T.set_output_mirrors(n, ptrs)); });
 }
 int rk_tree_set_option(rk_tree *t, const char *name, long long value)
 {

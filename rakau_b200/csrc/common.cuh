@@ -264,6 +264,7 @@ unsigned lf_scratch_doubles();
 // ---------------------------------------------------------------------------------------------------
 // Traversal (traverse.cu)
 // ---------------------------------------------------------------------------------------------------
+constexpr unsigned TRAV_MAX_MIRRORS = 8;
 template <typename F>
 struct trav_params {
     const vec4<F> *parts;
@@ -282,6 +283,10 @@ struct trav_params {
     // the caller's buffer itself (mapped into the device's address space), so no device-to-host copy follows the launch;
     // out[j] (device memory) still receives the partial sums phase 1 parks for phase 2, which are read back.
     F *outf[4];
+    // further copies of the output arrays that receive every final result (same index): the other ranks' peer-mapped
+    // buffers of a multi-GPU evaluation, a mapped host buffer ...
+    F *mirror[TRAV_MAX_MIRRORS][4];
+    u32 n_mirror;
     const u32 *perm; // non-null: ordered outputs (scatter through perm)
     u64 *group_cost; // per critical node (nullable)
     u64 *counters;   // 5 x u64: mac_tests, accepted, p2p_pairs, self_pairs, sum T*accepted (nullable)

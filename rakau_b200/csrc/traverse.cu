@@ -1030,16 +1030,27 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                         }
                     }
                     const F tmass = tpos[i].w;
+                    constexpr int NRES = Q == 0 ? 3 : (Q == 1 ? 1 : 4);
+                    F v[NRES];
                     if (Q == 0 || Q == 2) {
-                        __stcs(p.outf[0] + dst, a.x * p.G);
-                        __stcs(p.outf[1] + dst, a.y * p.G);
-                        __stcs(p.outf[2] + dst, a.z * p.G);
+                        v[0] = a.x * p.G;
+                        v[1] = a.y * p.G;
+                        v[2] = a.z * p.G;
                     }
-                    if (Q == 1) {
-                        __stcs(p.outf[0] + dst, (-tmass * a.w) * p.G);
+                    if (Q != 0) {
+                        v[NRES - 1] = (-tmass * a.w) * p.G;
                     }
-                    if (Q == 2) {
-                        __stcs(p.outf[3] + dst, (-tmass * a.w) * p.G);
+#pragma unroll
+                    for (int j = 0; j < NRES; ++j) {
+                        __stcs(p.outf[j] + dst, v[j]);
+                    }
+                    // copies of the output arrays on other devices (peer memory) or in mapped host memory: the exchange
+                    // of a multi-GPU evaluation happens here, store by store, underneath the arithmetic of the launch
+                    for (u32 r = 0; r < p.n_mirror; ++r) {
+#pragma unroll
+                        for (int j = 0; j < NRES; ++j) {
+                            __stcs(p.mirror[r][j] + dst, v[j]);
+                        }
                     }
                 }
             }

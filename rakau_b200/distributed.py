@@ -11,9 +11,16 @@ managed memory, src/rakau_cuda.cu:434-527, and its README admits poor scaling). 
 * traversal: contiguous Morton ranges of critical nodes, cut by the previous evaluation's interaction counts
   (rakau_b200.sharding); the output slices are all-gathered (padded to the largest slice).
 """
+import os
+
 import numpy as np
 
 from . import RK_DEVICE, RK_LAST_PERM, Octree, deduce_box, sharding
+
+
+def world_fits_mirrors(world):
+    """rk_tree_set_output_mirrors holds 8 mirrors: the peers of the rank plus, possibly, one pinned host slice."""
+    return world - 1 + 1 <= 8
 
 
 class ShardedTree:
@@ -44,6 +51,8 @@ class ShardedTree:
         # reference's split) instead of being thrown away.
         self.cut_pidx = None
         self._build_id, self._cuts_build_id = 0, -1
+        # output exchange by stores from inside the traversal kernel (True) or by copy-engine pushes of 4 chunked launches
+        self.mirror_exchange = os.environ.get("RK_MIRROR_EXCHANGE", "1") != "0" and world_fits_mirrors(self.world)
         self._side = None  # stream of the particle all-gather that runs underneath the topology build
         self._push = None  # per-peer copy streams of the output exchange
         self._peer = None  # two sets of (capacity, buffers, per-buffer list of every rank's device pointer), or False
@@ -462,6 +471,28 @@ class ShardedTree:
             return info, out
         _, bufs, ptrs = peer
         out = [b[:self.n] for b in bufs[:nres]]
+        if self.mirror_exchange:
+            # ONE launch over the whole range (a single tail, work stealing included) whose kernel stores every final
+            # result into its own buffer AND into each peer's (and into the pinned host slice, if asked for): the
+            # exchange rides on NVLink store by store underneath the arithmetic (rk_tree_set_output_mirrors).
+            esz = out[0].element_size()
+            mirrors = [[ptrs[j][r] for j in range(nres)] for r in range(self.world) if r != self.rank]
+            if host_out is not None:
+                pb = int(self.cut_particles[self.rank])
+                mirrors.append([host_out[j].data_ptr() - pb * esz for j in range(nres)])
+            self.tree.set_output_mirrors(mirrors)
+            try:
+                if c1 > c0:
+                    self.tree.acc_pot(Q, theta, G=G, eps=eps, out=out, where=RK_DEVICE, crit_range=(c0, c1))
+                    info = self.tree.eval_info.asdict()
+                else:
+                    from . import EvalInfo
+                    info = EvalInfo().asdict()
+            finally:
+                self.tree.set_output_mirrors([])
+            main = torch.cuda.current_stream()
+            self._stream_barrier(main)  # every rank's launch (and with it its stores) has completed
+            return info, out
         from . import device_copy_async
         nc = c1 - c0
         ccuts = sorted({c0, c1, *[c0 + int(nc * f) for f in chunks]})
