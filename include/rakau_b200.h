@@ -162,6 +162,11 @@ RK_API int rk_tree_build_presorted(rk_tree *t, const void *x, const void *y, con
  * (CUDA IPC / symmetric memory): the multi-GPU output exchange pushes finished result slices into every peer's
  * buffer with it while the next traversal launch occupies the SMs (an NCCL kernel would wait for them). */
 RK_API int rk_device_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+/* The same bytes to ndst <= 8 destinations (8-byte aligned like src; typically the same slice of every peer's buffer)
+ * with ONE kernel on `stream`: every 8-byte word is read once and stored ndst times, the remote stores travelling over
+ * NVLink. For the moments of the multi-GPU build when the SMs have nothing else to do (the all-gather of the bucket
+ * codes, which the topology needs before it can start). */
+RK_API int rk_device_bcast_copy(void *const *dst, unsigned ndst, const void *src, size_t bytes, void *stream);
 /* determine_box_size's final arithmetic (tree.hpp:1309-1312) for a global max |coordinate|. */
 RK_API double rk_deduce_box(int fp_bits, double absmax);
 /* Copy constructor / assignment (tree.hpp:1735-1743, 1785-1822): deep device-to-device copy of src into dst

@@ -32,7 +32,7 @@ SYMBOLS = [
     "rk_tree_update_masses", "rk_tree_clear", "rk_tree_nparts", "rk_tree_nnodes", "rk_tree_ncrit",
     "rk_tree_box_size", "rk_tree_get_parts", "rk_tree_get_codes", "rk_tree_get_perm", "rk_tree_get_nodes",
     "rk_tree_get_crit", "rk_tree_acc_pot", "rk_tree_acc_pot_range", "rk_tree_get_group_costs", "rk_tree_exact",
-    "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak", "rk_device_copy_async",
+    "rk_traverse_external_tree", "rk_tree_group_costs_device", "rk_kernel_launch_count", "rk_measure_fp32_peak", "rk_device_copy_async", "rk_device_bcast_copy",
     "rk_plummer", "rk_tree_clone", "rk_plummer_leapfrog", "rk_tree_get_parts_device", "rk_tree_get_perm_device",
     "rk_tree_sort_shard", "rk_tree_get_codes_device", "rk_tree_build_presorted", "rk_deduce_box", "rk_tree_crit_begin_at",
     "rk_tree_crit_lower_bound", "rk_tree_digest", "rk_tree_last_kernel", "rk_measure_fp64_peak", "rk_tree_set_option", "rk_tree_set_output_mirrors",
@@ -126,6 +126,7 @@ def lib():
     L.rk_tree_group_costs_device.argtypes = [vp]
     L.rk_kernel_launch_count.restype = C.c_ulonglong
     L.rk_device_copy_async.argtypes = [vp, vp, sz, vp]
+    L.rk_device_bcast_copy.argtypes = [C.POINTER(C.c_void_p), C.c_uint, vp, sz, vp]
     L.rk_measure_fp32_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.rk_plummer.argtypes = [i32, sz, sz, sz, dbl, dbl, i32, sz, i32, vp, vp, vp, vp]
     L.rk_plummer_leapfrog.argtypes = [i32, sz, dbl, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
@@ -421,6 +422,14 @@ def device_copy_async(dst_ptr, src_ptr, nbytes, stream_ptr):
     rc = lib().rk_device_copy_async(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nbytes, C.c_void_p(stream_ptr))
     if rc:
         raise RakauError(rc, "rk_device_copy_async failed")
+
+
+def device_bcast_copy(dst_ptrs, src_ptr, nbytes, stream_ptr):
+    """One kernel on the given cudaStream_t that copies nbytes from src to each of the (<= 8) destinations."""
+    arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+    rc = lib().rk_device_bcast_copy(arr, len(dst_ptrs), C.c_void_p(src_ptr), nbytes, C.c_void_p(stream_ptr))
+    if rc:
+        raise RakauError(rc, "rk_device_bcast_copy failed")
 
 
 def kernel_launch_count():

@@ -1132,6 +1132,44 @@ __global__ void __launch_bounds__(256) gather_u64_kernel(const u64 *__restrict__
     }
 }
 
+// One read, up to 8 writes: the same 8-byte words go to every destination (peer memory of the other ranks, reached
+// with plain stores over NVLink). Used where the SMs have nothing else to do - the codes of the sorted buckets must be
+// everywhere before the topology can start - and the copy engines, which serve 7 peers with fewer engines than
+// peers, measured 2.6 ms for what the links carry in 1.
+struct bcast_dst {
+    u64 *p[8];
+};
+__global__ void __launch_bounds__(256) bcast_copy_kernel(const u64 *__restrict__ src, bcast_dst d, int nd, size_t n8,
+                                                         const unsigned char *src_tail, size_t tail, size_t tail_off)
+{
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    for (; i + 3 * stride < n8; i += 4 * stride) { // four loads in flight per thread, then 4 x nd stores
+        const u64 v0 = __ldcs(src + i), v1 = __ldcs(src + i + stride), v2 = __ldcs(src + i + 2 * stride),
+                  v3 = __ldcs(src + i + 3 * stride);
+#pragma unroll 1
+        for (int k = 0; k < nd; ++k) {
+            u64 *q = d.p[k] + i;
+            __stcs(q, v0);
+            __stcs(q + stride, v1);
+            __stcs(q + 2 * stride, v2);
+            __stcs(q + 3 * stride, v3);
+        }
+    }
+    for (; i < n8; i += stride) {
+        const u64 v = __ldcs(src + i);
+#pragma unroll 1
+        for (int k = 0; k < nd; ++k) {
+            __stcs(d.p[k] + i, v);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < tail) { // the last bytes % 8
+        for (int k = 0; k < nd; ++k) {
+            reinterpret_cast<unsigned char *>(d.p[k])[tail_off + threadIdx.x] = src_tail[threadIdx.x];
+        }
+    }
+}
+
 // out[perm[i]] = in[i]: results from Morton order to the original particle order (tree.hpp:3320-3330).
 template <typename F>
 __global__ void __launch_bounds__(256)
@@ -1195,6 +1233,21 @@ void launch_bucket_ids(const u64 *codes, size_t n, const u64 *splitters, unsigne
     if (n) {
         bucket_ids_kernel<<<div_up(n, 256), 256, 0, st>>>(codes, n, splitters, nsplit, ids); count_launch();
     }
+}
+void launch_bcast_copy(void *const *dst, int nd, const void *src, size_t bytes, int sm_count, cudaStream_t st)
+{
+    if (!bytes || nd <= 0) {
+        return;
+    }
+    bcast_dst d{};
+    for (int k = 0; k < nd; ++k) {
+        d.p[k] = static_cast<u64 *>(dst[k]);
+    }
+    const size_t n8 = bytes / 8, tail = bytes % 8;
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>(size_t(sm_count) * 8, (n8 + 255) / 256 + 1));
+    bcast_copy_kernel<<<grid, 256, 0, st>>>(static_cast<const u64 *>(src), d, nd, n8,
+                                            static_cast<const unsigned char *>(src) + n8 * 8, tail, n8 * 8);
+    count_launch();
 }
 void launch_gather_u64(const u64 *in, const u32 *idx, u64 *out, size_t n, cudaStream_t st)
 {

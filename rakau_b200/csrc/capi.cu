@@ -2178,6 +2178,30 @@ int rk_device_copy_async(void *dst, const void *src, size_t bytes, void *stream)
                ? RK_OK
                : RK_ERR_RUNTIME;
 }
+int rk_device_bcast_copy(void *const *dst, unsigned ndst, const void *src, size_t bytes, void *stream)
+{
+    if (!bytes || !ndst) {
+        return RK_OK;
+    }
+    if (!dst || !src || ndst > 8 || (reinterpret_cast<uintptr_t>(src) & 7u)) {
+        return RK_ERR_INVALID_ARGUMENT;
+    }
+    for (unsigned k = 0; k < ndst; ++k) {
+        if (!dst[k] || (reinterpret_cast<uintptr_t>(dst[k]) & 7u)) {
+            return RK_ERR_INVALID_ARGUMENT;
+        }
+    }
+    try {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            return RK_ERR_RUNTIME;
+        }
+        rk::launch_bcast_copy(dst, static_cast<int>(ndst), src, bytes, sms, static_cast<cudaStream_t>(stream));
+        return cudaGetLastError() == cudaSuccess ? RK_OK : RK_ERR_RUNTIME;
+    } catch (...) {
+        return RK_ERR_RUNTIME;
+    }
+}
 unsigned long long rk_kernel_launch_count(void)
 {
     return __atomic_load_n(&rk::g_kernel_launches, __ATOMIC_RELAXED);

@@ -217,6 +217,8 @@ void launch_iota(u32 *p, size_t n, cudaStream_t st);
 // ids[i] = number of splitters <= codes[i] (the bucket of a sample sort, < 256); out[i] = in[idx[i]] for 64-bit words
 void launch_bucket_ids(const u64 *codes, size_t n, const u64 *splitters, unsigned nsplit, u64 *ids, cudaStream_t st);
 void launch_gather_u64(const u64 *in, const u32 *idx, u64 *out, size_t n, cudaStream_t st);
+// the same bytes to nd <= 8 destinations (8-byte aligned, like src) with one kernel: one read, nd stores per word
+void launch_bcast_copy(void *const *dst, int nd, const void *src, size_t bytes, int sm_count, cudaStream_t st);
 template <typename F>
 void launch_scatter_perm(const F *in, const u32 *perm, F *out, size_t n, cudaStream_t st);
 // out += sum over the 32-bit words w_i of the array of mix64(i, w_i): an order-independent fingerprint of a device array

@@ -53,6 +53,7 @@ class ShardedTree:
         self._build_id, self._cuts_build_id = 0, -1
         # output exchange by stores from inside the traversal kernel (True) or by copy-engine pushes of 4 chunked launches
         self.mirror_exchange = os.environ.get("RK_MIRROR_EXCHANGE", "1") != "0" and world_fits_mirrors(self.world)
+        self.bcast_codes = os.environ.get("RK_BCAST_CODES", "1") != "0"  # all-gather of the codes by one SM kernel
         self._side = None  # stream of the particle all-gather that runs underneath the topology build
         self._push = None  # per-peer copy streams of the output exchange
         self._peer = None  # two sets of (capacity, buffers, per-buffer list of every rank's device pointer), or False
@@ -292,9 +293,20 @@ class ShardedTree:
                     device_copy_async(ptrs[r] + off * esz, t.data_ptr(), n_b * esz, self._push[r].cuda_stream)
             return buf[:n]
 
-        fc = push('c', bc)
-        for s in self._push:
-            side.wait_stream(s)
+        if self.bcast_codes and n_b:
+            # the codes: ONE kernel stores this rank's bucket into every rank's full array (nothing else can run yet:
+            # the topology needs all the codes), instead of world copy-engine copies
+            from . import device_bcast_copy
+            side.wait_stream(main)
+            buf, ptrs = g['c']
+            order = [(self.rank + d) % self.world for d in range(self.world)]
+            for i in range(0, self.world, 8):
+                device_bcast_copy([ptrs[r] + off * 8 for r in order[i:i + 8]], bc.data_ptr(), n_b * 8, side.cuda_stream)
+            fc = buf[:n]
+        else:
+            fc = push('c', bc)
+            for s in self._push:
+                side.wait_stream(s)
         self._stream_barrier(side)
         codes_ready = torch.cuda.Event()
         codes_ready.record(side)
