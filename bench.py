@@ -597,7 +597,9 @@ def run_ours(args):
         "config": workload_config(args, nparts),
         "tree": {"interactions_per_step": inter, "n_nodes": bi["n_nodes"], "n_crit": bi["n_crit"],
                  "sharding": (f"sample_sort_build+morton_range_traversal_x{world}" if world > 1 else "single_gpu"),
-                 "shard_cost_imbalance": state["imbalance"]},
+                 "shard_cost_imbalance": state["imbalance"],
+                 "output_exchange": sharded.exchange_mode if sharded is not None else None,
+                 "codes_gather": sharded.codes_gather_mode if sharded is not None else None},
         "ms_build": b_ms, "ms_traverse_kernel": k_ms,
         "build_phases_ms": {k: bi[k] for k in ("ms_encode", "ms_sort", "ms_permute", "ms_topology", "ms_props")},
         "roofline": {"bound": "fp32", "kernel": kernel_name, "achieved": achieved,

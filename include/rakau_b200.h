@@ -120,8 +120,10 @@ RK_API int rk_tree_set_option(rk_tree *t, const char *name, long long value);
  * rk_tree_acc_pot / rk_tree_acc_pot_range with DEVICE outputs writes as well, at the same indices, from inside the
  * traversal kernel - the output exchange of a multi-GPU evaluation (each rank mirrors its range into its peers'
  * buffers over NVLink while it computes; src/rakau_cuda.cu:492-527 copies each device's slice back afterwards instead).
- * n = 0 switches it off. The caller orders the peers' reads after this call (a barrier across the ranks). */
-RK_API int rk_tree_set_output_mirrors(rk_tree *t, unsigned n, void *const *ptrs);
+ * n = 0 switches it off. The caller orders the peers' reads after this call (a barrier across the ranks).
+ * multicast_mask: bit r set = mirror r is an NVSwitch MULTICAST address (cuMulticast / symmetric memory): it is written
+ * with multimem.st, one store leaving the GPU and the switch updating every rank's copy. */
+RK_API int rk_tree_set_output_mirrors(rk_tree *t, unsigned n, void *const *ptrs, unsigned multicast_mask);
 
 /* ---- construction: construct_impl, tree.hpp:1329-1487 ------------------------------------------------ */
 /* Copies n particles (SoA x, y, z, m; host or device pointers) into the tree, deduces the box if
@@ -165,8 +167,9 @@ RK_API int rk_device_copy_async(void *dst, const void *src, size_t bytes, void *
 /* The same bytes to ndst <= 8 destinations (8-byte aligned like src; typically the same slice of every peer's buffer)
  * with ONE kernel on `stream`: every 8-byte word is read once and stored ndst times, the remote stores travelling over
  * NVLink. For the moments of the multi-GPU build when the SMs have nothing else to do (the all-gather of the bucket
- * codes, which the topology needs before it can start). */
-RK_API int rk_device_bcast_copy(void *const *dst, unsigned ndst, const void *src, size_t bytes, void *stream);
+ * codes, which the topology needs before it can start). multicast != 0: dst[0] (ndst == 1, bytes % 8 == 0) is an NVSwitch
+ * multicast address; every word leaves the GPU once (multimem.st) and the switch writes all the copies. */
+RK_API int rk_device_bcast_copy(void *const *dst, unsigned ndst, const void *src, size_t bytes, void *stream, int multicast);
 /* determine_box_size's final arithmetic (tree.hpp:1309-1312) for a global max |coordinate|. */
 RK_API double rk_deduce_box(int fp_bits, double absmax);
 /* Copy constructor / assignment (tree.hpp:1735-1743, 1785-1822): deep device-to-device copy of src into dst

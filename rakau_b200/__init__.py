@@ -126,7 +126,7 @@ def lib():
     L.rk_tree_group_costs_device.argtypes = [vp]
     L.rk_kernel_launch_count.restype = C.c_ulonglong
     L.rk_device_copy_async.argtypes = [vp, vp, sz, vp]
-    L.rk_device_bcast_copy.argtypes = [C.POINTER(C.c_void_p), C.c_uint, vp, sz, vp]
+    L.rk_device_bcast_copy.argtypes = [C.POINTER(C.c_void_p), C.c_uint, vp, sz, vp, C.c_int]
     L.rk_measure_fp32_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.rk_plummer.argtypes = [i32, sz, sz, sz, dbl, dbl, i32, sz, i32, vp, vp, vp, vp]
     L.rk_plummer_leapfrog.argtypes = [i32, sz, dbl, vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
@@ -142,7 +142,7 @@ def lib():
     L.rk_tree_digest.argtypes = [vp, vp]
     L.rk_tree_to_original_order.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     L.rk_tree_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
-    L.rk_tree_set_output_mirrors.argtypes = [vp, C.c_uint, C.POINTER(C.c_void_p)]
+    L.rk_tree_set_output_mirrors.argtypes = [vp, C.c_uint, C.POINTER(C.c_void_p), C.c_uint]
     L.rk_tree_leapfrog_init.argtypes = [vp, vp, vp, vp, i32, dbl, dbl, dbl, i32]
     L.rk_tree_leapfrog_step.argtypes = [vp, dbl, C.POINTER(LeapfrogInfo)]
     L.rk_tree_leapfrog_get.argtypes = [vp, i32, vp, vp, vp, i32]
@@ -210,14 +210,15 @@ class Octree:
     def synchronize(self):
         self._check(self.L.rk_tree_synchronize(self.h))
 
-    def set_output_mirrors(self, mirrors):
+    def set_output_mirrors(self, mirrors, multicast_mask=0):
         """mirrors: list (<= 8) of lists of integer device pointers / tensors, one per result array: further copies of
-        the outputs that the following device-output evaluations write from inside the kernel ([] = off)."""
+        the outputs that the following device-output evaluations write from inside the kernel ([] = off).
+        multicast_mask: bit r set = mirror r holds NVSwitch multicast addresses."""
         flat = (C.c_void_p * (4 * max(len(mirrors), 1)))()
         for r, arrs in enumerate(mirrors):
             for j, a in enumerate(arrs):
                 flat[4 * r + j] = _ptr(a)
-        self._check(self.L.rk_tree_set_output_mirrors(self.h, len(mirrors), flat))
+        self._check(self.L.rk_tree_set_output_mirrors(self.h, len(mirrors), flat, int(multicast_mask)))
 
     def set_option(self, name, value):
         self._check(self.L.rk_tree_set_option(self.h, name.encode(), int(value)))
@@ -424,10 +425,12 @@ def device_copy_async(dst_ptr, src_ptr, nbytes, stream_ptr):
         raise RakauError(rc, "rk_device_copy_async failed")
 
 
-def device_bcast_copy(dst_ptrs, src_ptr, nbytes, stream_ptr):
-    """One kernel on the given cudaStream_t that copies nbytes from src to each of the (<= 8) destinations."""
+def device_bcast_copy(dst_ptrs, src_ptr, nbytes, stream_ptr, multicast=False):
+    """One kernel on the given cudaStream_t that copies nbytes from src to each of the (<= 8) destinations; multicast:
+    the single destination is an NVSwitch multicast address."""
     arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
-    rc = lib().rk_device_bcast_copy(arr, len(dst_ptrs), C.c_void_p(src_ptr), nbytes, C.c_void_p(stream_ptr))
+    rc = lib().rk_device_bcast_copy(arr, len(dst_ptrs), C.c_void_p(src_ptr), nbytes, C.c_void_p(stream_ptr),
+                                    1 if multicast else 0)
     if rc:
         raise RakauError(rc, "rk_device_bcast_copy failed")
 

@@ -1139,6 +1139,27 @@ __global__ void __launch_bounds__(256) gather_u64_kernel(const u64 *__restrict__
 struct bcast_dst {
     u64 *p[8];
 };
+__device__ __forceinline__ void multimem_store_u64(u64 *mc, u64 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(mc), "l"(v) : "memory");
+}
+// d.p[0] is an NVSwitch multicast address: one store per word leaves the GPU and the switch updates every rank's copy
+__global__ void __launch_bounds__(256) mcast_copy_kernel(const u64 *__restrict__ src, u64 *mc, size_t n8)
+{
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    for (; i + 3 * stride < n8; i += 4 * stride) {
+        const u64 v0 = __ldcs(src + i), v1 = __ldcs(src + i + stride), v2 = __ldcs(src + i + 2 * stride),
+                  v3 = __ldcs(src + i + 3 * stride);
+        multimem_store_u64(mc + i, v0);
+        multimem_store_u64(mc + i + stride, v1);
+        multimem_store_u64(mc + i + 2 * stride, v2);
+        multimem_store_u64(mc + i + 3 * stride, v3);
+    }
+    for (; i < n8; i += stride) {
+        multimem_store_u64(mc + i, __ldcs(src + i));
+    }
+}
 __global__ void __launch_bounds__(256) bcast_copy_kernel(const u64 *__restrict__ src, bcast_dst d, int nd, size_t n8,
                                                          const unsigned char *src_tail, size_t tail, size_t tail_off)
 {
@@ -1234,9 +1255,16 @@ void launch_bucket_ids(const u64 *codes, size_t n, const u64 *splitters, unsigne
         bucket_ids_kernel<<<div_up(n, 256), 256, 0, st>>>(codes, n, splitters, nsplit, ids); count_launch();
     }
 }
-void launch_bcast_copy(void *const *dst, int nd, const void *src, size_t bytes, int sm_count, cudaStream_t st)
+void launch_bcast_copy(void *const *dst, int nd, const void *src, size_t bytes, int sm_count, cudaStream_t st, bool multicast)
 {
     if (!bytes || nd <= 0) {
+        return;
+    }
+    if (multicast) { // (bytes % 8 == 0 checked by the caller)
+        const size_t n8 = bytes / 8;
+        const unsigned grid = static_cast<unsigned>(std::min<size_t>(size_t(sm_count) * 4, (n8 + 255) / 256));
+        mcast_copy_kernel<<<grid, 256, 0, st>>>(static_cast<const u64 *>(src), static_cast<u64 *>(dst[0]), n8);
+        count_launch();
         return;
     }
     bcast_dst d{};

@@ -745,6 +745,7 @@ public:
                 }
             }
             p.n_mirror = m_n_mirror;
+            p.mirror_multicast = m_mirror_multicast;
         }
         RK_CUDA_CHECK(cudaEventRecord(m_ev.ev[4], m_stream));
         RK_CUDA_CHECK(cudaMemsetAsync(m_work.p, 0, 8 * sizeof(u32), m_stream));
@@ -1472,8 +1473,9 @@ public:
     const char *last_kernel() const { return m_kernel_name; }
     // Copies of the output arrays (device-accessible: peer memory, mapped host memory) that the following evaluations
     // with DEVICE outputs write as well, result by result, from inside the traversal kernel.
-    void set_output_mirrors(unsigned n, void *const *ptrs)
+    void set_output_mirrors(unsigned n, void *const *ptrs, unsigned multicast_mask)
     {
+        m_mirror_multicast = multicast_mask;
         if (n > TRAV_MAX_MIRRORS || (n && !ptrs)) {
             throw api_error(RK_ERR_INVALID_ARGUMENT, "rk_tree_set_output_mirrors: at most " + std::to_string(TRAV_MAX_MIRRORS)
                                                          + " mirrors of 4 pointers each");
@@ -1836,7 +1838,7 @@ private:
     dbuf<u64> m_group_cost, m_counters;
     dbuf<u32> m_work, m_steal;
     F *m_out_mirror[TRAV_MAX_MIRRORS][4] = {};
-    unsigned m_n_mirror = 0; // rk_tree_set_output_mirrors
+    unsigned m_n_mirror = 0, m_mirror_multicast = 0; // rk_tree_set_output_mirrors
     int m_zero_copy_out = 1; // rk_tree_set_option("zero_copy_out"): final results straight into pinned host outputs
     dbuf<u64> m_ids_sorted; // partition_shard scratch
     bool m_costs_valid = false, m_have_inv = false, m_pending_check_encode = false;
@@ -2138,9 +2140,9 @@ int rk_tree_leapfrog_get(rk_tree *t, int what, void *a, void *b, void *c, int wh
 {
     return guarded(t, [&]() { RK_WITH(t, T.leapfrog_get(what, a, b, c, where)); });
 }
-int rk_tree_set_output_mirrors(rk_tree *t, unsigned n, void *const *ptrs)
+int rk_tree_set_output_mirrors(rk_tree *t, unsigned n, void *const *ptrs, unsigned multicast_mask)
 {
-    return guarded(t, [&]() { RK_WITH(t, T.set_output_mirrors(n, ptrs)); });
+    return guarded(t, [&]() { RK_WITH(t, T.set_output_mirrors(n, ptrs, multicast_mask)); });
 }
 int rk_tree_set_option(rk_tree *t, const char *name, long long value)
 {
@@ -2178,10 +2180,13 @@ int rk_device_copy_async(void *dst, const void *src, size_t bytes, void *stream)
                ? RK_OK
                : RK_ERR_RUNTIME;
 }
-int rk_device_bcast_copy(void *const *dst, unsigned ndst, const void *src, size_t bytes, void *stream)
+int rk_device_bcast_copy(void *const *dst, unsigned ndst, const void *src, size_t bytes, void *stream, int multicast)
 {
     if (!bytes || !ndst) {
         return RK_OK;
+    }
+    if (multicast && (ndst != 1 || bytes % 8)) {
+        return RK_ERR_INVALID_ARGUMENT;
     }
     if (!dst || !src || ndst > 8 || (reinterpret_cast<uintptr_t>(src) & 7u)) {
         return RK_ERR_INVALID_ARGUMENT;
@@ -2196,7 +2201,7 @@ int rk_device_bcast_copy(void *const *dst, unsigned ndst, const void *src, size_
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
             return RK_ERR_RUNTIME;
         }
-        rk::launch_bcast_copy(dst, static_cast<int>(ndst), src, bytes, sms, static_cast<cudaStream_t>(stream));
+        rk::launch_bcast_copy(dst, static_cast<int>(ndst), src, bytes, sms, static_cast<cudaStream_t>(stream), multicast != 0);
         return cudaGetLastError() == cudaSuccess ? RK_OK : RK_ERR_RUNTIME;
     } catch (...) {
         return RK_ERR_RUNTIME;

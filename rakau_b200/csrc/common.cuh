@@ -218,7 +218,9 @@ void launch_iota(u32 *p, size_t n, cudaStream_t st);
 void launch_bucket_ids(const u64 *codes, size_t n, const u64 *splitters, unsigned nsplit, u64 *ids, cudaStream_t st);
 void launch_gather_u64(const u64 *in, const u32 *idx, u64 *out, size_t n, cudaStream_t st);
 // the same bytes to nd <= 8 destinations (8-byte aligned, like src) with one kernel: one read, nd stores per word
-void launch_bcast_copy(void *const *dst, int nd, const void *src, size_t bytes, int sm_count, cudaStream_t st);
+// multicast: dst[0] is an NVSwitch multicast address (bytes % 8 == 0), written once with multimem.st
+void launch_bcast_copy(void *const *dst, int nd, const void *src, size_t bytes, int sm_count, cudaStream_t st,
+                       bool multicast = false);
 template <typename F>
 void launch_scatter_perm(const F *in, const u32 *perm, F *out, size_t n, cudaStream_t st);
 // out += sum over the 32-bit words w_i of the array of mix64(i, w_i): an order-independent fingerprint of a device array
@@ -289,6 +291,7 @@ struct trav_params {
     // buffers of a multi-GPU evaluation, a mapped host buffer ...
     F *mirror[TRAV_MAX_MIRRORS][4];
     u32 n_mirror;
+    u32 mirror_multicast; // bit r: mirror r is an NVSwitch multicast address (written with multimem.st)
     const u32 *perm; // non-null: ordered outputs (scatter through perm)
     u64 *group_cost; // per critical node (nullable)
     u64 *counters;   // 5 x u64: mac_tests, accepted, p2p_pairs, self_pairs, sum T*accepted (nullable)

@@ -110,6 +110,14 @@ __device__ __forceinline__ void cp_async_vec4(double4 *dst, const double4 *src)
     cp_async_16(reinterpret_cast<char *>(dst) + 16, reinterpret_cast<const char *>(src) + 16);
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void multimem_store(float *mc, float v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_store(double *mc, double v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+}
 
 // MUFU.RSQ without the denormal pre/post-scaling of rsqrtf() (a squared distance below 1e-38 is not a
 // meaningful input; it flushes to zero exactly like a coincident pair).
@@ -1047,9 +1055,17 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                     // copies of the output arrays on other devices (peer memory) or in mapped host memory: the exchange
                     // of a multi-GPU evaluation happens here, store by store, underneath the arithmetic of the launch
                     for (u32 r = 0; r < p.n_mirror; ++r) {
+                        if ((p.mirror_multicast >> r) & 1u) {
+                            // an NVSwitch multicast address: one store leaves the GPU, the switch writes every rank's copy
 #pragma unroll
-                        for (int j = 0; j < NRES; ++j) {
-                            __stcs(p.mirror[r][j] + dst, v[j]);
+                            for (int j = 0; j < NRES; ++j) {
+                                multimem_store(p.mirror[r][j] + dst, v[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NRES; ++j) {
+                                __stcs(p.mirror[r][j] + dst, v[j]);
+                            }
                         }
                     }
                 }

@@ -18,6 +18,14 @@ import numpy as np
 from . import RK_DEVICE, RK_LAST_PERM, Octree, deduce_box, sharding
 
 
+def _multicast_ptr(handle):
+    """NVSwitch multicast address of a symmetric-memory buffer (0: the platform has none)."""
+    try:
+        return int(getattr(handle, "multicast_ptr", 0) or 0)
+    except Exception:  # noqa: BLE001
+        return 0
+
+
 def world_fits_mirrors(world):
     """rk_tree_set_output_mirrors holds 8 mirrors: the peers of the rank plus, possibly, one pinned host slice."""
     return world - 1 + 1 <= 8
@@ -53,7 +61,12 @@ class ShardedTree:
         self._build_id, self._cuts_build_id = 0, -1
         # output exchange by stores from inside the traversal kernel (True) or by copy-engine pushes of 4 chunked launches
         self.mirror_exchange = os.environ.get("RK_MIRROR_EXCHANGE", "1") != "0" and world_fits_mirrors(self.world)
-        self.bcast_codes = os.environ.get("RK_BCAST_CODES", "1") != "0"  # all-gather of the codes by one SM kernel
+        # NVSwitch multicast stores where the platform has them and there are enough peers for them to pay: between two
+        # ranks a multicast store is just a slower store (measured: codes gather 1.24 ms against 0.51 ms for the copy
+        # engine, evaluation + exchange 18.45 against 18.28 ms)
+        mc_env = os.environ.get("RK_MULTICAST", "auto")
+        self.multicast = mc_env == "1" or (mc_env == "auto" and self.world > 2)
+        self.exchange_mode = self.codes_gather_mode = None
         self._side = None  # stream of the particle all-gather that runs underneath the topology build
         self._push = None  # per-peer copy streams of the output exchange
         self._peer = None  # two sets of (capacity, buffers, per-buffer list of every rank's device pointer), or False
@@ -267,6 +280,7 @@ class ShardedTree:
                     t = symm_mem.empty(cap, dtype=dtp, device=self.dev)
                     h = symm_mem.rendezvous(t, dist.group.WORLD)
                     g[k] = (t, [int(p) for p in h.buffer_ptrs])
+                    g['mc_' + k] = _multicast_ptr(h)
                 self._gpeer = g
             except Exception as exc:  # noqa: BLE001
                 self._gpeer = False
@@ -293,17 +307,17 @@ class ShardedTree:
                     device_copy_async(ptrs[r] + off * esz, t.data_ptr(), n_b * esz, self._push[r].cuda_stream)
             return buf[:n]
 
-        if self.bcast_codes and n_b:
-            # the codes: ONE kernel stores this rank's bucket into every rank's full array (nothing else can run yet:
-            # the topology needs all the codes), instead of world copy-engine copies
+        if self.multicast and g['mc_c'] and n_b:
+            # the codes: ONE kernel stores this rank's bucket through the NVSwitch multicast address of the full array -
+            # every word leaves the GPU once and lands in every rank's copy (nothing else can run yet: the topology needs
+            # all the codes). Plain stores to each of 7 peers measured 4.3 ms against 2.6 ms for the copy engines.
             from . import device_bcast_copy
             side.wait_stream(main)
-            buf, ptrs = g['c']
-            order = [(self.rank + d) % self.world for d in range(self.world)]
-            for i in range(0, self.world, 8):
-                device_bcast_copy([ptrs[r] + off * 8 for r in order[i:i + 8]], bc.data_ptr(), n_b * 8, side.cuda_stream)
-            fc = buf[:n]
+            device_bcast_copy([g['mc_c'] + off * 8], bc.data_ptr(), n_b * 8, side.cuda_stream, multicast=True)
+            fc = g['c'][0][:n]
+            self.codes_gather_mode = "multicast kernel"
         else:
+            self.codes_gather_mode = "copy-engine pushes"
             fc = push('c', bc)
             for s in self._push:
                 side.wait_stream(s)
@@ -413,14 +427,17 @@ class ShardedTree:
                 import torch.distributed._symmetric_memory as symm_mem
                 cap = int(self.n * 1.02) + 16
                 sets = []
+                self._peer_mc = []
                 for _ in range(2):
-                    bufs, ptrs = [], []
+                    bufs, ptrs, mcs = [], [], []
                     for _ in range(max(nres, 3)):
                         t = symm_mem.empty(cap, dtype=self.dt, device=self.dev)
                         h = symm_mem.rendezvous(t, self.dist.group.WORLD)
                         bufs.append(t)
                         ptrs.append([int(p) for p in h.buffer_ptrs])
+                        mcs.append(_multicast_ptr(h))
                     sets.append((cap, bufs, ptrs))
+                    self._peer_mc.append(mcs)
                 self._peer = sets
             except Exception as exc:  # noqa: BLE001 - no peer memory on this platform: use the collective path
                 self._peer = False
@@ -483,16 +500,24 @@ class ShardedTree:
             return info, out
         _, bufs, ptrs = peer
         out = [b[:self.n] for b in bufs[:nres]]
-        if self.mirror_exchange:
+        mc = self._peer_mc[self._peer_flip][:nres] if self.multicast else []
+        use_mc = bool(mc) and all(mc)
+        # (stores to 7 peers from inside the kernel cost more than they save - measured at 8 GPUs: the kernel 23.5 ms
+        # instead of 19.3 - so without multicast the in-kernel exchange is used between two ranks only)
+        if self.mirror_exchange and (use_mc or self.world <= 2):
             # ONE launch over the whole range (a single tail, work stealing included) whose kernel stores every final
             # result into its own buffer AND into each peer's (and into the pinned host slice, if asked for): the
             # exchange rides on NVLink store by store underneath the arithmetic (rk_tree_set_output_mirrors).
             esz = out[0].element_size()
-            mirrors = [[ptrs[j][r] for j in range(nres)] for r in range(self.world) if r != self.rank]
+            if use_mc:
+                mirrors, mask = [list(mc)], 1  # one multicast store per result: the switch writes every rank's copy
+            else:
+                mirrors, mask = [[ptrs[j][r] for j in range(nres)] for r in range(self.world) if r != self.rank], 0
             if host_out is not None:
                 pb = int(self.cut_particles[self.rank])
                 mirrors.append([host_out[j].data_ptr() - pb * esz for j in range(nres)])
-            self.tree.set_output_mirrors(mirrors)
+            self.tree.set_output_mirrors(mirrors, mask)
+            self.exchange_mode = "in-kernel multicast stores" if use_mc else "in-kernel peer stores"
             try:
                 if c1 > c0:
                     self.tree.acc_pot(Q, theta, G=G, eps=eps, out=out, where=RK_DEVICE, crit_range=(c0, c1))
@@ -505,6 +530,7 @@ class ShardedTree:
             main = torch.cuda.current_stream()
             self._stream_barrier(main)  # every rank's launch (and with it its stores) has completed
             return info, out
+        self.exchange_mode = "copy-engine pushes of 4 launches"
         from . import device_copy_async
         nc = c1 - c0
         ccuts = sorted({c0, c1, *[c0 + int(nc * f) for f in chunks]})

@@ -336,3 +336,56 @@ def test_pinned_host_outputs_are_written_by_the_kernel(oracle_mod, rk, Q):
     assert g.eval_info.kernel_launches == 4
     for j in range(nres):
         assert (pn[j] == ref[j]).all(), j
+
+
+def test_output_mirrors_receive_every_result(oracle_mod, rk):
+    """rk_tree_set_output_mirrors: the kernel stores each final result into the mirrors as well (on one GPU: two device
+    buffers and a pinned host buffer shifted by the first particle of the range, as the multi-GPU exchange uses
+    them). Mirrors equal the outputs inside the evaluated range and stay untouched outside it."""
+    import torch
+    n = 300000
+    m, x, y, z = oracle_mod.plummer(n)
+    g = rk.Octree()
+    g.build(x, y, z, m)
+    C = g.ncrit_nodes
+    c0, c1 = 11, C - 5
+    lo, hi = (int(v) for v in g.crit_begin_at([c0, c1]))
+    out = [torch.full((n,), float("nan"), device="cuda") for _ in range(4)]
+    mir = [[torch.full((n,), float("nan"), device="cuda") for _ in range(4)] for _ in range(2)]
+    host = [torch.full((hi - lo,), float("nan")).pin_memory() for _ in range(4)]
+    g.set_output_mirrors([[t.data_ptr() for t in mir[0]], [t.data_ptr() for t in mir[1]],
+                          [t.data_ptr() - 4 * lo for t in host]])
+    g.acc_pot(2, 0.75, eps=0.001, out=out, where=rk.RK_DEVICE, crit_range=(c0, c1))
+    g.set_output_mirrors([])
+    torch.cuda.synchronize()
+    for j in range(4):
+        o = out[j].cpu().numpy()
+        assert np.isfinite(o[lo:hi]).all() and np.isnan(o[:lo]).all() and np.isnan(o[hi:]).all()
+        for r in range(2):
+            mm = mir[r][j].cpu().numpy()
+            assert (mm[lo:hi] == o[lo:hi]).all() and np.isnan(mm[:lo]).all() and np.isnan(mm[hi:]).all()
+        assert (host[j].numpy() == o[lo:hi]).all()
+    # switched off again: the mirrors keep their old contents
+    for t in mir[0]:
+        t.fill_(7.0)
+    g.acc_pot(2, 0.75, eps=0.001, out=out, where=rk.RK_DEVICE)
+    torch.cuda.synchronize()
+    assert all(bool((t == 7.0).all()) for t in mir[0])
+    with pytest.raises(rk.RakauError):
+        g.set_output_mirrors([[0, 0, 0, 0]] * 9)
+
+
+def test_bcast_copy(rk):
+    """rk_device_bcast_copy: the same bytes to several destinations, odd 8-byte offsets and a tail that is not a
+    multiple of 8 bytes included."""
+    import torch
+    src = torch.randint(0, 255, (8 * 100003 + 5,), dtype=torch.uint8, device="cuda")
+    dst = [torch.zeros(8 * 100010 + 64, dtype=torch.uint8, device="cuda") for _ in range(5)]
+    offs = [0, 8, 24, 8 * 7, 16]
+    rk.device_bcast_copy([d.data_ptr() + o for d, o in zip(dst, offs)], src.data_ptr(), src.numel(),
+                         torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for d, o in zip(dst, offs):
+        assert bool((d[o:o + src.numel()] == src).all()) and int(d[:o].sum()) == 0 and int(d[o + src.numel():].sum()) == 0
+    with pytest.raises(rk.RakauError):
+        rk.device_bcast_copy([dst[0].data_ptr() + 4], src.data_ptr(), 64, 0)

@@ -9,7 +9,7 @@ for ln in open('gpurun_out/n8_bench8.json'):
     if ln.startswith('{'):
         d=json.loads(ln)
         print('parity', d['parity_checked'], d['parity'])
-        print('ms_per_step', d['ms_per_step'], 'value', d['value'], 'build', d['ms_build'], 'trav+exch', d['ms_traverse_and_exchange'], 'e2e', d['e2e']['ms_per_step'])
+        print(d['tree'].get('output_exchange'), d['tree'].get('codes_gather')); print('ms_per_step', d['ms_per_step'], 'value', d['value'], 'build', d['ms_build'], 'trav+exch', d['ms_traverse_and_exchange'], 'e2e', d['e2e']['ms_per_step'])
         print('phases rank0', d['build_phases_rank0_ms'])
         print('kernel per rank', d['ms_traverse_kernel_per_rank'])
         print('replicated phases', d['build_phases_ms'], 'imbalance', d['tree']['shard_cost_imbalance'])

@@ -9,5 +9,5 @@ import json
 for ln in open('gpurun_out/n2_bench2.json'):
     if ln.startswith('{'):
         d=json.loads(ln)
-        print(d['parity_checked'], d['ms_per_step'], d['ms_build'], d['ms_traverse_and_exchange'], d['build_phases_rank0_ms'], d['ms_traverse_kernel_per_rank'], d['e2e']['ms_per_step'])
+        print(d['tree'].get('output_exchange'), d['tree'].get('codes_gather'), d['parity_checked'], d['ms_per_step'], d['ms_build'], d['ms_traverse_and_exchange'], d['build_phases_rank0_ms'], d['ms_traverse_kernel_per_rank'], d['e2e']['ms_per_step'])
 PY
