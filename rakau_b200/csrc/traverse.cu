@@ -998,9 +998,12 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                 }
             }
 
-            // Combine the slices' partial sums (fixed shuffle tree: deterministic). Phase 1 parks the run's partial
-            // sums in the output arrays; a group adds them to its own, applies G as one final multiply
-            // (tree.hpp:2986-3002) and writes out (3004-3007).
+            // Combine the slices' partial sums (fixed shuffle tree: deterministic) and put the totals back into the
+            // accumulator area in TARGET order, so that the write-back below runs over consecutive targets with all 32
+            // lanes: full 128-byte stores (which matters most for the mirrors, whose stores cross NVLink) instead of P
+            // lanes per slot. Phase 1 parks the run's partial sums in the output arrays; a group adds them to its own,
+            // applies G as one final multiply (tree.hpp:2986-3002) and writes out (3004-3007).
+            vec4<F> *const accb = ph1 ? tgt : acc;
             for (u32 k = 0; k < rr; ++k) {
                 vec4<F> a = acc_lane[32u * k];
                 for (u32 o = P; o < 32u; o <<= 1) {
@@ -1009,8 +1012,18 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                     a.z += __shfl_xor_sync(FULL, a.z, o);
                     a.w += __shfl_xor_sync(FULL, a.w, o);
                 }
-                const u32 i = t0 + P * k + tl;
-                if (sl == 0u && i < t0 + tc && (!ph1 || (gb + i >= fb && gb + i < fe))) { // (phase 1: in-range targets only)
+                // (slot k of every lane has been read: the shuffles are warp-wide. Target P * k + tl lies in a slot <= k)
+                if (sl == 0u && P * k + tl < tc) {
+                    accb[P * k + tl] = a;
+                }
+            }
+            __syncwarp();
+            for (u32 i = t0 + static_cast<u32>(lane); i < t0 + tc; i += 32u) {
+                if (ph1 && !(gb + i >= fb && gb + i < fe)) { // (phase 1: in-range targets only)
+                    continue;
+                }
+                vec4<F> a = accb[i - t0];
+                {
                     u32 dst = gb + i;
                     if (p.perm) {
                         dst = p.perm[dst];
@@ -1070,6 +1083,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                     }
                 }
             }
+            __syncwarp();
             if (!ph1 && t0 == 0 && lane == 0) {
                 const u32 t_mac = n_mac + rs[RS_MAC1], t_acc = n_acc + rs[RS_ACC1], t_p2p = n_p2p + rs[RS_P2P1];
                 if (p.group_cost) {

@@ -66,6 +66,7 @@ class ShardedTree:
         # engine, evaluation + exchange 18.45 against 18.28 ms)
         mc_env = os.environ.get("RK_MULTICAST", "auto")
         self.multicast = mc_env == "1" or (mc_env == "auto" and self.world > 2)
+        self.multicast_codes = os.environ.get("RK_MULTICAST_CODES", "0") == "1"
         self.exchange_mode = self.codes_gather_mode = None
         self._side = None  # stream of the particle all-gather that runs underneath the topology build
         self._push = None  # per-peer copy streams of the output exchange
@@ -307,10 +308,10 @@ class ShardedTree:
                     device_copy_async(ptrs[r] + off * esz, t.data_ptr(), n_b * esz, self._push[r].cuda_stream)
             return buf[:n]
 
-        if self.multicast and g['mc_c'] and n_b:
+        if self.multicast_codes and g['mc_c'] and n_b:
             # the codes: ONE kernel stores this rank's bucket through the NVSwitch multicast address of the full array -
-            # every word leaves the GPU once and lands in every rank's copy (nothing else can run yet: the topology needs
-            # all the codes). Plain stores to each of 7 peers measured 4.3 ms against 2.6 ms for the copy engines.
+            # every word leaves the GPU once and lands in every rank's copy. Measured at 8 GPUs (128 MB per rank): 3.1 ms,
+            # plain stores to each of the 7 peers 4.3 ms, the copy engines 2.6 ms - so this is off unless asked for.
             from . import device_bcast_copy
             side.wait_stream(main)
             device_bcast_copy([g['mc_c'] + off * 8], bc.data_ptr(), n_b * 8, side.cuda_stream, multicast=True)
