@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _two_ranks(extra):
+def _two_ranks(extra, env=None):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -21,7 +21,7 @@ def _two_ranks(extra):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "2",
            "--warmup", "3", "--nparts", "3000000"] + extra
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -33,6 +33,19 @@ def test_two_rank_result_equals_single_gpu():
     assert d["n_gpus"] == 2 and d["parity_checked"] is True, d.get("parity")
     assert d["parity"]["tree_arrays_differing"] == [] and d["parity"]["accelerations_bit_equal"] is True
     assert d["parity"]["max_abs_diff"] == 0.0
+
+
+@pytest.mark.parametrize("env,mode", [({"RK_MULTICAST": "1", "RK_MULTICAST_CODES": "1"}, "in-kernel multicast stores"),
+                                      ({"RK_MIRROR_EXCHANGE": "0"}, "copy-engine pushes of 4 launches")])
+def test_two_rank_other_exchange_schemes(env, mode):
+    """The output exchange has three implementations (in-kernel stores to each peer: the default between two ranks;
+    NVSwitch multicast stores: the default for more; copy-engine pushes of four chunked launches: the fallback without
+    peer-mapped stores); all of them - and the multicast gather of the codes - must reproduce the single-GPU result."""
+    d = _two_ranks(["--perturb"], env)
+    if d["tree"]["output_exchange"] != mode:
+        pytest.skip("this platform has no NVSwitch multicast: " + str(d["tree"]["output_exchange"]))
+    assert d["parity_checked"] is True, d.get("parity")
+    assert d["parity"]["accelerations_bit_equal"] is True and d["parity"]["tree_arrays_differing"] == []
 
 
 def test_two_rank_cuts_survive_moving_particles():
