@@ -296,6 +296,7 @@ struct trav_params {
     u64 *group_cost; // per critical node (nullable)
     u64 *counters;   // 5 x u64: mac_tests, accepted, p2p_pairs, self_pairs, sum T*accepted (nullable)
     u32 tmax;        // targets staged in shared memory per warp
+    u32 ring;        // entries of the source ring per warp (set by launch_traverse)
     u32 *err;        // stack overflow flag
     u32 out_offset;  // subtracted from the particle index when writing (external-tree drop-in)
     u32 window;      // two-phase walk: particles per run of sibling groups (trav_window()); 0 = one group per unit

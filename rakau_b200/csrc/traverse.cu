@@ -52,6 +52,15 @@ namespace
 
 constexpr int TRAV_WARPS = 4;
 constexpr int TRAV_THREADS = TRAV_WARPS * 32;
+#ifndef RK_RING_RESET
+#define RK_RING_RESET 1
+#endif
+#ifndef RK_RING_GROW
+#define RK_RING_GROW 1
+#endif
+#ifndef RK_RING_ROOM
+#define RK_RING_ROOM 32 // 32: the scratch block aliases the step's append area; 64: it lies behind it
+#endif
 #ifndef RK_UNROLL
 #define RK_UNROLL 4
 #endif
@@ -439,11 +448,23 @@ template <typename F, int Q, int MAC, int BATCH_>
 __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : RK_CTAS) traverse_kernel(const trav_params<F> p)
 {
     constexpr u32 BATCH = BATCH_, LCAP = 2 * BATCH_;
+    // Ring discipline. RESET (rings of >= 128 entries): the walk fills the ring up to TH = LCAP - 32 entries (one step
+    // appends <= 32 more; the step's scratch block is the same 32 entries, used before the step's appends are written),
+    // the consume step evaluates EVERYTHING that is there and the ring starts again at entry 0 - batches of 224+ sources
+    // instead of 128 for the same shared memory, i.e. 40 % fewer tile prologues / accumulator round trips. Otherwise
+    // (the 64-entry ring of the large-tmax configurations): batches of exactly BATCH sources from a circular ring, the
+    // scratch block BATCH entries after its head.
+    // In RESET mode nothing needs a power of two, so the ring takes whatever shared memory the resident CTAs leave
+    // unused (p.ring entries >= LCAP, chosen in launch_one()).
+    constexpr bool RESET = RK_RING_RESET && BATCH_ >= 64;
+    const u32 lcap = RESET ? p.ring : LCAP;
+    const u32 TH = RESET ? lcap - RK_RING_ROOM : BATCH;
+    auto ridx = [&](u32 i) { return RESET ? i : (i & (LCAP - 1)); };
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *base = smem_raw + size_t(warp) * warp_smem_bytes<F>(p.tmax, LCAP);
+    unsigned char *base = smem_raw + size_t(warp) * warp_smem_bytes<F>(p.tmax, lcap);
     vec4<F> *ring = reinterpret_cast<vec4<F> *>(base);
-    vec4<F> *tgt = ring + LCAP;
+    vec4<F> *tgt = ring + lcap;
     vec4<F> *acc = tgt + p.tmax;
     u32 *stack = reinterpret_cast<u32 *>(acc + acc_entries(p.tmax));
     const u32 rr_cap = acc_entries(p.tmax) / 32u;              // accumulator slots per lane (one group)
@@ -712,10 +733,10 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
 
             for (;;) {
                 // ---------------- produce: fill the ring until >= 32 sources or the walk is over -------------
-                while (lcount < BATCH && !done) {
+                while (lcount < TH && !done) {
                     if (lq_done < lq_total) {
                         // copy more particles of the rejected leaves into the ring
-                        const u32 room = LCAP - lcount, rem = lq_total - lq_done;
+                        const u32 room = lcap - lcount, rem = lq_total - lq_done;
                         const u32 chunk = rem < room ? rem : room;
                         for (u32 f = lq_done + lane; f < lq_done + chunk; f += 32) {
                             int lo = 0;
@@ -726,7 +747,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                                 }
                             }
                             const u32 pidx = lq_base[lo] + f;
-                            cp_async_vec4(&ring[(lhead + lcount + (f - lq_done)) & (LCAP - 1)], p.parts + pidx);
+                            cp_async_vec4(&ring[ridx(lhead + lcount + (f - lq_done))], p.parts + pidx);
                         }
                         __syncwarp(); // (the copies stay in flight until the next consume step)
                         lcount += chunk;
@@ -830,7 +851,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                             // the 32 lanes share the targets of ONE node at a time (broadcast LDS.128 per node)
                             const u32 m_need = __ballot_sync(FULL, need);
                             const u32 n_need = __popc(m_need), my_slot = __popc(m_need & ltm);
-                            vec4<F> *amb = ring + ((lhead + BATCH) & (LCAP - 1)); // a free 32-entry block (lcount < BATCH here)
+                            // a free 32-entry block (lcount < TH here)
+                            vec4<F> *amb = ring + (RESET ? (RK_RING_ROOM == 32 ? lcount : TH + 32u) : ridx(lhead + BATCH));
                             if (need) {
                                 amb[my_slot] = make_vec4<F>(na.x, na.y, na.z, mac_lh);
                             }
@@ -913,7 +935,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                     }
                     // accepted nodes -> ring
                     if (accept) {
-                        ring[(lhead + lcount + __popc(m_acc & ltm)) & (LCAP - 1)] = na;
+                        ring[ridx(lhead + lcount + __popc(m_acc & ltm))] = na;
                     }
                     lcount += __popc(m_acc);
                     // rejected internal nodes / ancestors -> stack
@@ -947,7 +969,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                     break;
                 }
                 // ---------------- consume: evaluate up to 32 sources (the only ring call site) ----------------
-                const u32 ne = lcount < BATCH ? lcount : BATCH;
+                const u32 ne = (RESET || lcount < BATCH) ? lcount : BATCH;
                 cp_async_wait_all(); // leaf particles still in flight
                 __syncwarp();
                 if (RK_SKIP_EVAL && p.G != F(-12345)) {
@@ -960,7 +982,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                     eval_slots<F, Q, false>(ring + lhead, ne, sl, 5u - lp, eps2, tpos, T, t0 + tl, P, rr, acc_lane);
                 }
                 __syncwarp();
-                lhead = (lhead + ne) & (LCAP - 1);
+                lhead = RESET ? 0u : ridx(lhead + ne);
                 lcount -= ne;
             }
             if (overflow && lane == 0) {
@@ -1222,9 +1244,9 @@ __global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, doubl
 }
 
 template <typename F, int Q, int MAC, int BATCH>
-int trav_occupancy(u32 tmax, size_t &smem)
+int trav_occupancy(u32 tmax, size_t &smem, u32 ring = 2 * BATCH)
 {
-    smem = warp_smem_bytes<F>(tmax, 2 * BATCH) * TRAV_WARPS;
+    smem = warp_smem_bytes<F>(tmax, ring) * TRAV_WARPS;
     int per_sm = 0;
     if (cudaFuncSetAttribute(traverse_kernel<F, Q, MAC, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem))
@@ -1247,9 +1269,29 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *na
     const int occ64 = trav_occupancy<F, Q, MAC, BIG>(p.tmax, smem64), occ32 = trav_occupancy<F, Q, MAC, 32>(p.tmax, smem32);
     const bool big = occ64 >= occ32 && occ64 > 0;
     int per_sm = big ? occ64 : occ32;
+    // the ring of the BIG variant takes the shared memory its resident CTAs leave unused (RESET mode of the kernel)
+    u32 ring = 2 * BIG;
+    if (big && RK_RING_RESET && RK_RING_GROW) {
+        static u32 cached_tmax = 0, cached_ring = 0; // (per instantiation; occupancy depends on tmax only)
+        if (cached_tmax != p.tmax) {
+            u32 r = ring;
+            size_t sm = 0;
+            while (r + 32u <= 1024u && trav_occupancy<F, Q, MAC, BIG>(p.tmax, sm, r + 32u) == occ64) {
+                r += 32u;
+            }
+            cached_tmax = p.tmax;
+            cached_ring = r;
+        }
+        ring = cached_ring;
+        if (trav_occupancy<F, Q, MAC, BIG>(p.tmax, smem64, ring) != occ64) { // (sets the attribute for this size)
+            throw cuda_error(1, "inconsistent occupancy of the traversal kernel");
+        }
+    }
+    trav_params<F> q = p;
+    q.ring = ring;
     if (name) {
-        std::snprintf(name, 96, "traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> window=%u ctas_per_sm=%d",
-                      sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? BIG : 32, p.window, per_sm);
+        std::snprintf(name, 96, "traverse_kernel<%s,Q=%d,MAC=%d,BATCH=%d> window=%u ctas_per_sm=%d ring=%u",
+                      sizeof(F) == 4 ? "float" : "double", Q, MAC, big ? BIG : 32, p.window, per_sm, big ? ring : 64u);
     }
     static const bool debug = std::getenv("RK_DEBUG_LAUNCH") != nullptr;
     if (debug) {
@@ -1270,9 +1312,9 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *na
         return;
     }
     if (big) {
-        traverse_kernel<F, Q, MAC, BIG><<<grid, TRAV_THREADS, smem64, st>>>(p);
+        traverse_kernel<F, Q, MAC, BIG><<<grid, TRAV_THREADS, smem64, st>>>(q);
     } else {
-        traverse_kernel<F, Q, MAC, 32><<<grid, TRAV_THREADS, smem32, st>>>(p);
+        traverse_kernel<F, Q, MAC, 32><<<grid, TRAV_THREADS, smem32, st>>>(q);
     }
     count_launch();
     RK_CUDA_CHECK(cudaGetLastError());
