@@ -724,7 +724,7 @@ public:
             p.steal = m_steal.p;
             p.steal_published = m_steal.p + size_t(TRAV_STEAL_SLOTS) * 16;
             p.steal_front = p.steal_published + 16;
-            p.steal_k = TRAV_STEAL_SLOTS;
+            p.steal_k = trav_steal_k();
             RK_CUDA_CHECK(cudaMemsetAsync(m_steal.p, 0, (size_t(TRAV_STEAL_SLOTS) * 16 + 16) * sizeof(u32), m_stream));
         }
         for (int j = 0; j < nres; ++j) {
@@ -1076,7 +1076,7 @@ public:
             p.steal = m_steal.p;
             p.steal_published = m_steal.p + size_t(TRAV_STEAL_SLOTS) * 16;
             p.steal_front = p.steal_published + 16;
-            p.steal_k = TRAV_STEAL_SLOTS;
+            p.steal_k = trav_steal_k();
             RK_CUDA_CHECK(cudaMemsetAsync(m_steal.p, 0, (size_t(TRAV_STEAL_SLOTS) * 16 + 16) * sizeof(u32), m_stream));
         }
         const int nres = Q == 0 ? 3 : (Q == 1 ? 1 : 4);

@@ -305,7 +305,9 @@ struct trav_params {
     u32 *steal, *steal_front, *steal_published;
     u32 steal_k;
 };
-constexpr unsigned TRAV_STEAL_SLOTS = 2048;
+constexpr unsigned TRAV_STEAL_SLOTS = 2048; // records allocated
+// records used: the runs of the last wave that publish themselves (RK_STEAL_K in the environment overrides it: tuning)
+unsigned trav_steal_k();
 // words per stolen frontier = the per-warp stack capacity of traverse.cu
 unsigned trav_stack_cap();
 // Window of the two-phase walk for groups of at most max_group targets (0 when a group exceeds the staging area).

@@ -1326,6 +1326,15 @@ void launch_one(const trav_params<F> &p, int sm_count, cudaStream_t st, char *na
 #define RK_TWO_PHASE 1
 #endif
 unsigned trav_stack_cap() { return STACK_CAP; }
+unsigned trav_steal_k()
+{
+    static const unsigned k = [] {
+        const char *e = std::getenv("RK_STEAL_K");
+        const long v = e ? std::atol(e) : 2048;
+        return static_cast<unsigned>(v < 0 ? 0 : (v > long(TRAV_STEAL_SLOTS) ? long(TRAV_STEAL_SLOTS) : v));
+    }();
+    return k;
+}
 
 u32 trav_window(u32 tmax, size_t max_group)
 {
