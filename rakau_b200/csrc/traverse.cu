@@ -1029,6 +1029,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
             // lanes per slot. Phase 1 parks the run's partial sums in the output arrays; a group adds them to its own,
             // applies G as one final multiply (tree.hpp:2986-3002) and writes out (3004-3007).
             vec4<F> *const accb = ph1 ? tgt : acc;
+            __syncwarp(); // the accumulator stores of the evaluation loops above are ordered before the re-layout
             for (u32 k = 0; k < rr; ++k) {
                 vec4<F> a = acc_lane[32u * k];
                 for (u32 o = P; o < 32u; o <<= 1) {
@@ -1037,7 +1038,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, sizeof(F) == 8 ? RK_F64_CTAS : R
                     a.z += __shfl_xor_sync(FULL, a.z, o);
                     a.w += __shfl_xor_sync(FULL, a.w, o);
                 }
-                // (slot k of every lane has been read: the shuffles are warp-wide. Target P * k + tl lies in a slot <= k)
+                // slot k of every lane has been read; target P * k + tl lies in a slot <= k, i.e. in one nobody reads again
+                __syncwarp();
                 if (sl == 0u && P * k + tl < tc) {
                     accb[P * k + tl] = a;
                 }
